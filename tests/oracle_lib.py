@@ -1,0 +1,157 @@
+"""ctypes wrapper of the CPU oracle (oracle/libzso.so).  Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "libzso.so")
+
+_lib = None
+
+
+class BlockTrace(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int), ("last", ctypes.c_int), ("n_symbols", ctypes.c_int),
+                ("stored_len", ctypes.c_int), ("bit_start", ctypes.c_uint64)]
+
+
+BLOCK_CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(BlockTrace), ctypes.POINTER(ctypes.c_uint16),
+                            ctypes.POINTER(ctypes.c_uint8))
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in
+                ("inserts", "searches", "chain_steps", "compare_bytes", "literals", "matches", "match_bytes", "blocks")]
+
+
+def build():
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("zso_deflate.c", "zso_inflate.c", "zso_adler32.c", "zso.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return LIB
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+
+    def bound(self, n, seg):
+        return self.lib.zso_deflate_bound(n, seg)
+
+    def deflate_oneshot(self, data, level, strategy=0, hv=0):
+        cap = self.bound(len(data), 0)
+        out = ctypes.create_string_buffer(cap)
+        n = ctypes.c_size_t(0)
+        ad = ctypes.c_uint32(0)
+        rc = self.lib.zso_deflate_oneshot(data, len(data), level, strategy, hv, out, cap, ctypes.byref(n), ctypes.byref(ad))
+        assert rc == 0, rc
+        return out.raw[:n.value], ad.value
+
+    def deflate_segments(self, data, seg_size, level, strategy=0, hv=0):
+        """-> (stream bytes, [segment end offsets], adler)"""
+        nseg = (len(data) + seg_size - 1) // seg_size
+        cap = self.bound(len(data), seg_size)
+        out = ctypes.create_string_buffer(cap)
+        n = ctypes.c_size_t(0)
+        ad = ctypes.c_uint32(0)
+        ends = (ctypes.c_uint64 * max(nseg, 1))()
+        rc = self.lib.zso_deflate_segments(data, len(data), seg_size, level, strategy, hv, out, cap, ctypes.byref(n),
+                                           ends, ctypes.byref(ad))
+        assert rc == 0, rc
+        return out.raw[:n.value], list(ends[:nseg]), ad.value
+
+    def trace_segments(self, data, seg_size, level, strategy=0, hv=0):
+        """Runs the segmented compressor with the block trace on.
+        -> (stream, ends, per-segment list of blocks: dict(type, n, stored_len, bit_start, sym=[(dist, lc)...]))"""
+        d = self.lib.zso_deflater_new(level, strategy, 3, hv)
+        assert d
+        segs, cur = [], []
+
+        def cb(_u, blk, dist, lc):
+            b = blk.contents
+            cur.append(dict(type=b.type, n=b.n_symbols, stored_len=b.stored_len, bit_start=b.bit_start,
+                            sym=[(dist[i], lc[i]) for i in range(b.n_symbols)]))
+
+        cbf = BLOCK_CB(cb)
+        self.lib.zso_deflater_set_trace(d, cbf, None)
+        ends = []
+        for off in range(0, len(data), seg_size):
+            chunk = data[off:off + seg_size]
+            assert self.lib.zso_deflater_write(d, chunk, len(chunk)) == 0
+            ends.append(self.lib.zso_deflater_total_out(d))
+            segs.append(cur)
+            cur = []
+        assert self.lib.zso_deflater_finish(d) == 0
+        n = ctypes.c_size_t(0)
+        p = self.lib.zso_deflater_output(d, ctypes.byref(n))
+        out = ctypes.string_at(p, n.value)
+        self.lib.zso_deflater_free(d)
+        return out, ends, segs
+
+    def counters(self, data, seg_size, level, strategy=0, hv=0):
+        d = self.lib.zso_deflater_new(level, strategy, 3 if seg_size else 0, hv)
+        step = seg_size or max(len(data), 1)
+        for off in range(0, len(data), step):
+            chunk = data[off:off + step]
+            assert self.lib.zso_deflater_write(d, chunk, len(chunk)) == 0
+        assert self.lib.zso_deflater_finish(d) == 0
+        c = Counters()
+        self.lib.zso_deflater_counters(d, ctypes.byref(c))
+        tot = self.lib.zso_deflater_total_out(d)
+        self.lib.zso_deflater_free(d)
+        return {n: getattr(c, n) for n, _ in Counters._fields_}, tot
+
+    def inflate(self, comp, out_cap):
+        out = ctypes.create_string_buffer(max(out_cap, 1))
+        n = ctypes.c_size_t(0)
+        used = ctypes.c_size_t(0)
+        ad = ctypes.c_uint32(0)
+        msg = ctypes.c_char_p()
+        rc = self.lib.zso_inflate(comp, len(comp), out, out_cap, ctypes.byref(n), ctypes.byref(used), ctypes.byref(ad),
+                                  ctypes.byref(msg))
+        return rc, out.raw[:n.value], ad.value, (msg.value or b"").decode(), used.value
+
+    def adler32(self, data, seed=1):
+        return self.lib.zso_adler32(seed, data, len(data))
+
+    def adler32_combine(self, a1, a2, len2):
+        return self.lib.zso_adler32_combine(a1, a2, len2)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = ctypes.CDLL(LIB)
+        c = ctypes
+        lib.zso_deflate_bound.restype = c.c_size_t
+        lib.zso_deflate_bound.argtypes = [c.c_size_t, c.c_size_t]
+        lib.zso_deflate_oneshot.argtypes = [c.c_char_p, c.c_size_t, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t,
+                                            c.POINTER(c.c_size_t), c.POINTER(c.c_uint32)]
+        lib.zso_deflate_segments.argtypes = [c.c_char_p, c.c_size_t, c.c_size_t, c.c_int, c.c_int, c.c_int, c.c_void_p,
+                                             c.c_size_t, c.POINTER(c.c_size_t), c.POINTER(c.c_uint64),
+                                             c.POINTER(c.c_uint32)]
+        lib.zso_deflater_new.restype = c.c_void_p
+        lib.zso_deflater_new.argtypes = [c.c_int] * 4
+        lib.zso_deflater_free.argtypes = [c.c_void_p]
+        lib.zso_deflater_set_trace.argtypes = [c.c_void_p, BLOCK_CB, c.c_void_p]
+        lib.zso_deflater_write.argtypes = [c.c_void_p, c.c_char_p, c.c_size_t]
+        lib.zso_deflater_finish.argtypes = [c.c_void_p]
+        lib.zso_deflater_output.restype = c.c_void_p
+        lib.zso_deflater_output.argtypes = [c.c_void_p, c.POINTER(c.c_size_t)]
+        lib.zso_deflater_total_out.restype = c.c_uint64
+        lib.zso_deflater_total_out.argtypes = [c.c_void_p]
+        lib.zso_deflater_total_in.restype = c.c_uint64
+        lib.zso_deflater_total_in.argtypes = [c.c_void_p]
+        lib.zso_deflater_adler.restype = c.c_uint32
+        lib.zso_deflater_adler.argtypes = [c.c_void_p]
+        lib.zso_deflater_counters.argtypes = [c.c_void_p, c.POINTER(Counters)]
+        lib.zso_inflate.argtypes = [c.c_char_p, c.c_size_t, c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t),
+                                    c.POINTER(c.c_size_t), c.POINTER(c.c_uint32), c.POINTER(c.c_char_p)]
+        lib.zso_adler32.restype = c.c_uint32
+        lib.zso_adler32.argtypes = [c.c_uint32, c.c_char_p, c.c_size_t]
+        lib.zso_adler32_combine.restype = c.c_uint32
+        lib.zso_adler32_combine.argtypes = [c.c_uint32, c.c_uint32, c.c_uint64]
+        _lib = Oracle(lib)
+    return _lib

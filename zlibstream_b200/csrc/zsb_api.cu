@@ -1,0 +1,604 @@
+// zsb_api.cu -- the C ABI of libzsb200 (include/zsb200.h): context, scratch memory, kernel orchestration.
+//
+// Host-side counterpart of ZLibStream (ZlibStream.cs) + Deflate.Compress / Inflate.Decompress control flow,
+// reduced to what a full-flush-segmented stream needs.  No CPU fallback: every entry point needs a device.
+#include "../../include/zsb200.h"
+#include "zsb_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace zsb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Deflate.cs:80-98
+const LevelCfg kLevels[10] = {{0, 0, 0, 0, FN_STORED},    {4, 4, 8, 4, FN_FAST},        {4, 5, 16, 8, FN_FAST},
+                              {4, 6, 32, 32, FN_FAST},    {4, 4, 16, 16, FN_SLOW},      {8, 16, 32, 32, FN_SLOW},
+                              {8, 16, 128, 128, FN_SLOW}, {8, 32, 128, 256, FN_SLOW},   {32, 128, 258, 1024, FN_SLOW},
+                              {32, 258, 258, 4096, FN_SLOW}};
+
+const char* const kInflateMsg[] = {  // Inflate.cs / InflateBlocks.cs / InfTree.cs / InfCodes.cs wording
+    "",
+    "invalid block type",
+    "invalid stored block lengths",
+    "too many length or distance symbols",
+    "invalid bit length repeat",
+    "oversubscribed dynamic bit lengths tree",
+    "incomplete dynamic bit lengths tree",
+    "oversubscribed literal/length tree",
+    "incomplete literal/length tree",
+    "oversubscribed distance tree",
+    "incomplete distance tree",
+    "empty distance tree with lengths",
+    "invalid literal/length code",
+    "invalid distance code",
+    "invalid distance too far back",
+    "buffer error",
+    "buffer error",
+    "segment does not decode to the segment size"};
+
+}  // namespace
+
+struct zsb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // scratch
+    DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status;
+    uint16_t* crc_tab = nullptr;
+    // timing of the last call
+    std::vector<cudaEvent_t> ev;  // pairs
+    std::vector<int> ev_kind;     // 0 lz77, 1 huffman, 2 inflate
+    float ms[3] = {0, 0, 0};
+    bool ms_valid = true;
+};
+
+namespace {
+
+int fail(zsb_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+int cuda_fail(zsb_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, e == cudaErrorMemoryAllocation ? ZSB_MEM_ERROR : ZSB_ERRNO, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                  \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+void crc32c_slices(uint16_t* out /* 4*256 */)
+{
+    uint32_t t[4][256];
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+        t[0][i] = c;
+    }
+    for (int s = 1; s < 4; s++)
+        for (uint32_t i = 0; i < 256; i++) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+    // crc32c(0, b0 | b1<<8 | b2<<16 | b3<<24) = t[3][b0] ^ t[2][b1] ^ t[1][b2] ^ t[0][b3]
+    for (uint32_t i = 0; i < 256; i++) {
+        out[i] = (uint16_t)t[3][i];
+        out[256 + i] = (uint16_t)t[2][i];
+        out[512 + i] = (uint16_t)t[1][i];
+        out[768 + i] = (uint16_t)t[0][i];
+    }
+}
+
+void timing_begin(zsb_ctx* c)
+{
+    for (auto e : c->ev) cudaEventDestroy(e);
+    c->ev.clear();
+    c->ev_kind.clear();
+    c->ms[0] = c->ms[1] = c->ms[2] = 0;
+    c->ms_valid = false;
+}
+void timing_mark(zsb_ctx* c, int kind, bool start)
+{
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->ev.push_back(e);
+    if (start) c->ev_kind.push_back(kind);
+}
+void timing_collect(zsb_ctx* c)
+{
+    if (c->ms_valid) return;
+    for (size_t i = 0; i + 1 < c->ev.size(); i += 2) {
+        float m = 0;
+        if (cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->ms[c->ev_kind[i / 2]] += m;
+    }
+    c->ms_valid = true;
+}
+
+__global__ void finalize_stream_kernel(uint8_t* out, size_t out_cap, uint64_t* total_out, const uint32_t* adler,
+                                       int write_header, uint32_t header, int write_trailer, int* status)
+{
+    // zlib header (Deflate.cs:464-493) and, for Finish, the final empty static block `03 00` followed by the
+    // big-endian Adler-32 (Deflate.cs:627-635)
+    if (*status != 0) return;
+    if (write_header) {
+        out[0] = (uint8_t)(header >> 8);
+        out[1] = (uint8_t)header;
+    }
+    if (write_trailer) {
+        uint64_t o = *total_out;
+        if (o + 6 > out_cap) { *status = ZSB_BUF_ERROR; *total_out = o + 6; return; }
+        const uint32_t a = *adler;
+        out[o] = 0x03;
+        out[o + 1] = 0x00;
+        out[o + 2] = (uint8_t)(a >> 24);
+        out[o + 3] = (uint8_t)(a >> 16);
+        out[o + 4] = (uint8_t)(a >> 8);
+        out[o + 5] = (uint8_t)a;
+        *total_out = o + 6;
+    }
+}
+
+size_t env_size(const char* name, size_t dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (size_t)strtoull(v, nullptr, 10);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* zsb_version(void) { return "zsb200 0.1.0 sm_100a"; }
+
+int zsb_ctx_create(int device, zsb_ctx** out)
+{
+    if (!out) return ZSB_STREAM_ERROR;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return ZSB_ERRNO;
+    zsb_ctx* ctx = new zsb_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return ZSB_ERRNO; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ZSB_ERRNO; }
+    if (prop.major < 10) { delete ctx; return ZSB_VERSION_ERROR; }  // built for sm_100a only
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ZSB_ERRNO; }
+    ctx->stream = ctx->own_stream;
+    uint16_t tab[1024];
+    crc32c_slices(tab);
+    if (cudaMalloc(&ctx->crc_tab, sizeof tab) != cudaSuccess ||
+        cudaMemcpy(ctx->crc_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess ||
+        ctx->small.reserve(256) != cudaSuccess) {
+        zsb_ctx_destroy(ctx);
+        return ZSB_MEM_ERROR;
+    }
+    *out = ctx;
+    return ZSB_OK;
+}
+
+void zsb_ctx_destroy(zsb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->ev) cudaEventDestroy(e);
+    DevBuf* bufs[] = {&ctx->in_stage, &ctx->out_stage, &ctx->sym, &ctx->blocks, &ctx->nblocks, &ctx->codes, &ctx->layout,
+                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->crc_tab) cudaFree(ctx->crc_tab);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* zsb_last_error(const zsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int zsb_ctx_set_stream(zsb_ctx* ctx, void* s)
+{
+    if (!ctx) return ZSB_STREAM_ERROR;
+    ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream;
+    return ZSB_OK;
+}
+void* zsb_ctx_get_stream(const zsb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t zsb_ctx_launch_count(const zsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zsb_ctx_last_kernel_ms(const zsb_ctx* cctx, float* lz, float* hf, float* inf)
+{
+    zsb_ctx* ctx = const_cast<zsb_ctx*>(cctx);
+    if (!ctx) return ZSB_STREAM_ERROR;
+    cudaStreamSynchronize(ctx->stream);
+    timing_collect(ctx);
+    if (lz) *lz = ctx->ms[0];
+    if (hf) *hf = ctx->ms[1];
+    if (inf) *inf = ctx->ms[2];
+    return ZSB_OK;
+}
+
+size_t zsb_deflate_bound(size_t n, size_t seg_size)
+{
+    const size_t segs = seg_size ? (n + seg_size - 1) / seg_size : 1;
+    // worst case: every block stored (5 bytes per <= 16383 symbols = bytes), per segment up to ~16 bytes of
+    // empty blocks and markers, header and trailer
+    return n + (n / 16383 + segs + 1) * 5 + segs * 24 + 16;
+}
+
+int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size, int level, int strategy,
+                         int hash_variant, uint64_t first_segment_index, const void* halo, unsigned flags, void* out,
+                         size_t out_cap, size_t* out_len, uint64_t* seg_end_offsets, uint32_t* adler)
+{
+    if (!ctx) return ZSB_STREAM_ERROR;
+    ctx->err.clear();
+    if (out_len) *out_len = 0;
+    // argument checks mirror Deflate's constructor (Deflate.cs:241-281)
+    if (level == -1) level = 6;
+    if (level < 0 || level > 9) return fail(ctx, ZSB_STREAM_ERROR, "level");
+    if (strategy < 0 || strategy > ZSB_FIXED) return fail(ctx, ZSB_STREAM_ERROR, "strategy");
+    if (hash_variant != ZSB_HASH_CRC32C && hash_variant != ZSB_HASH_MUL) return fail(ctx, ZSB_STREAM_ERROR, "hash_variant");
+    if ((n && !in) || !out) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
+    if (seg_size < 65536 || (seg_size & 32767) != 0 || seg_size > (64u << 20))
+        return fail(ctx, ZSB_STREAM_ERROR, "seg_size must be a multiple of 32768, >= 65536 and <= 64 MiB");
+    if (level == 0 && strategy != ZSB_RLE)
+        return fail(ctx, ZSB_STREAM_ERROR, "level 0 (stored) is not implemented on the device path");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    timing_begin(ctx);
+
+    const bool write_header = !(flags & ZSB_NO_HEADER);
+    const bool write_trailer = !(flags & ZSB_NO_TRAILER);
+    const size_t nseg = (n + seg_size - 1) / seg_size;
+    if (nseg > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "too many segments");
+
+    // ---- device views of input / output ----
+    const uint8_t* d_in = reinterpret_cast<const uint8_t*>(in);
+    if (!(flags & ZSB_IN_DEVICE) && n) {
+        CU(ctx->in_stage.reserve(n));
+        CU(cudaMemcpyAsync(ctx->in_stage.p, in, n, cudaMemcpyHostToDevice, st));
+        d_in = ctx->in_stage.as<uint8_t>();
+    }
+    const uint8_t* d_halo = reinterpret_cast<const uint8_t*>(halo);
+    if (halo && !(flags & ZSB_IN_DEVICE)) {
+        CU(ctx->halo_stage.reserve(W_SIZE));
+        CU(cudaMemcpyAsync(ctx->halo_stage.p, halo, W_SIZE, cudaMemcpyHostToDevice, st));
+        d_halo = ctx->halo_stage.as<uint8_t>();
+    }
+    if (first_segment_index == 0) d_halo = nullptr;
+    uint8_t* d_out = reinterpret_cast<uint8_t*>(out);
+    if (!(flags & ZSB_OUT_DEVICE)) {
+        CU(ctx->out_stage.reserve(out_cap ? out_cap : 1));
+        d_out = ctx->out_stage.as<uint8_t>();
+    }
+    uint64_t* d_seg_end = nullptr;
+    if (seg_end_offsets && nseg) {
+        if (flags & ZSB_OFFSETS_DEVICE) d_seg_end = seg_end_offsets;
+        else {
+            CU(ctx->seg_end.reserve(nseg * sizeof(uint64_t)));
+            d_seg_end = ctx->seg_end.as<uint64_t>();
+        }
+    }
+
+    // small device scalars: [0] total_out (u64), [8] status (int), [12] adler (u32), [16] work counter (u32)
+    uint8_t* small = ctx->small.as<uint8_t>();
+    uint64_t* d_total = reinterpret_cast<uint64_t*>(small);
+    int* d_status = reinterpret_cast<int*>(small + 8);
+    uint32_t* d_adler = reinterpret_cast<uint32_t*>(small + 12);
+    unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
+    struct { uint64_t total; int status; uint32_t adler; uint32_t work; } init = {write_header ? 2u : 0u, 0, 1u, 0u};
+    CU(cudaMemcpyAsync(small, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    if (out_cap < (size_t)(write_header ? 2 : 0)) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+
+    CU(ctx->seg_adler.reserve((nseg ? nseg : 1) * sizeof(uint2)));
+
+    // ---- batches of segments: bounded symbol scratch ----
+    const size_t sym_bytes_per_seg = seg_size * sizeof(uint32_t);
+    const uint32_t max_blocks = (uint32_t)(seg_size / BLOCK_SYMS + 2);
+    const size_t per_seg = sym_bytes_per_seg + max_blocks * (sizeof(BlockRec) + sizeof(BlockCodesDev)) + sizeof(uint32_t) + sizeof(SegLayout);
+    size_t budget = env_size("ZSB_SCRATCH_BYTES", (size_t)8 << 30);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const size_t have = free_b + ctx->sym.cap + ctx->blocks.cap + ctx->codes.cap;
+        if (budget > have / 2) budget = have / 2;
+    }
+    size_t batch = budget / per_seg;
+    if (batch < 1) batch = 1;
+    if (batch > nseg) batch = nseg;
+    if (nseg) {
+        CU(ctx->sym.reserve(batch * sym_bytes_per_seg));
+        CU(ctx->blocks.reserve(batch * max_blocks * sizeof(BlockRec)));
+        CU(ctx->codes.reserve(batch * max_blocks * sizeof(BlockCodesDev)));
+        CU(ctx->nblocks.reserve(batch * sizeof(uint32_t)));
+        CU(ctx->layout.reserve(batch * sizeof(SegLayout)));
+    }
+
+    const LevelCfg cfg = kLevels[level];
+    for (size_t s0 = 0; s0 < nseg; s0 += batch) {
+        const uint32_t cnt = (uint32_t)((nseg - s0) < batch ? (nseg - s0) : batch);
+        Lz77Params L;
+        L.in = d_in + s0 * seg_size;
+        L.n = n - s0 * seg_size;
+        L.seg_size = (uint32_t)seg_size;
+        L.nseg = cnt;
+        L.first_seg_index = first_segment_index + s0;
+        L.halo = s0 == 0 ? d_halo : nullptr;
+        L.strategy = strategy;
+        L.hash_variant = hash_variant;
+        L.good = cfg.good; L.lazy = cfg.lazy; L.nice = cfg.nice; L.chain = cfg.chain;
+        L.fn = strategy == ZSB_RLE ? FN_RLE : cfg.fn;
+        L.sym = ctx->sym.as<uint32_t>();
+        L.sym_stride = seg_size;
+        L.blocks = ctx->blocks.as<BlockRec>();
+        L.max_blocks = max_blocks;
+        L.nblocks = ctx->nblocks.as<uint32_t>();
+        L.seg_adler = ctx->seg_adler.as<uint2>() + s0;
+        L.work_counter = d_work;
+        L.crc_tab = ctx->crc_tab;
+        CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+        timing_mark(ctx, 0, true);
+        CU(launch_lz77(L, ctx->num_sms, st));
+        timing_mark(ctx, 0, false);
+        ctx->launches++;
+
+        HuffParams H;
+        H.in = L.in;
+        H.n = L.n;
+        H.seg_size = L.seg_size;
+        H.nseg = cnt;
+        H.first_seg_index = L.first_seg_index;
+        H.strategy = strategy;
+        H.sym = L.sym;
+        H.sym_stride = L.sym_stride;
+        H.blocks = L.blocks;
+        H.max_blocks = max_blocks;
+        H.nblocks = L.nblocks;
+        H.codes = ctx->codes.as<BlockCodesDev>();
+        H.layout = ctx->layout.as<SegLayout>();
+        H.out_base = 0;  // layout_kernel reads the running total from *total_out
+        H.total_out = d_total;
+        H.seg_end = d_seg_end ? d_seg_end + s0 : nullptr;
+        H.out = d_out;
+        H.out_cap = out_cap;
+        H.status = d_status;
+        timing_mark(ctx, 1, true);
+        CU(launch_block_trees(H, st));
+        CU(launch_layout(H, st));
+        CU(launch_pack(H, st));
+        timing_mark(ctx, 1, false);
+        ctx->launches += 3;
+    }
+    // ---- Adler-32 of the whole input, header, trailer ----
+    CU(launch_adler_fold(ctx->seg_adler.as<uint2>(), (uint32_t)nseg, (uint32_t)seg_size, n, 1u, d_adler, st));
+    ctx->launches++;
+    // Deflate.cs:466-480 (Q11): old-zlib FLEVEL, no strategy adjustment
+    uint32_t header = (8u + ((15u - 8u) << 4)) << 8;
+    uint32_t level_flags = ((uint32_t)(level - 1) & 0xff) >> 1;
+    if (level_flags > 3) level_flags = 3;
+    header |= level_flags << 6;
+    header += 31 - (header % 31);
+    finalize_stream_kernel<<<1, 1, 0, st>>>(d_out, out_cap, d_total, d_adler, write_header ? 1 : 0, header,
+                                            write_trailer ? 1 : 0, d_status);
+    CU(cudaGetLastError());
+    ctx->launches++;
+
+    struct { uint64_t total; int status; uint32_t adler; } fin;
+    CU(cudaMemcpyAsync(&fin, small, sizeof fin, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (out_len) *out_len = (size_t)fin.total;
+    if (adler) *adler = fin.adler;
+    if (fin.status != 0 || fin.total > out_cap) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+    if (!(flags & ZSB_OUT_DEVICE) && fin.total) CU(cudaMemcpyAsync(out, d_out, fin.total, cudaMemcpyDeviceToHost, st));
+    if (seg_end_offsets && nseg && !(flags & ZSB_OFFSETS_DEVICE))
+        CU(cudaMemcpyAsync(seg_end_offsets, d_seg_end, nseg * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ZSB_OK;
+}
+
+int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t* seg_end_offsets, size_t nseg,
+                         size_t seg_size, unsigned flags, void* out, size_t out_cap, size_t* out_len, uint32_t* adler)
+{
+    if (!ctx) return ZSB_STREAM_ERROR;
+    ctx->err.clear();
+    if (out_len) *out_len = 0;
+    if (!in || (!out && out_cap)) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
+    if (seg_size == 0 || seg_size > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "seg_size");
+    if (!seg_end_offsets) return fail(ctx, ZSB_STREAM_ERROR, "segment index scan is not implemented yet: pass seg_end_offsets");
+    if (nseg > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "too many segments");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    timing_begin(ctx);
+    const bool has_header = !(flags & ZSB_NO_HEADER), has_trailer = !(flags & ZSB_NO_TRAILER);
+
+    // ---- header checks on the host (Inflate.cs:120-178) need the first two bytes ----
+    uint8_t hdr[2] = {0, 0};
+    const uint8_t* d_in = reinterpret_cast<const uint8_t*>(in);
+    if (!(flags & ZSB_IN_DEVICE)) {
+        CU(ctx->in_stage.reserve(n ? n : 1));
+        CU(cudaMemcpyAsync(ctx->in_stage.p, in, n, cudaMemcpyHostToDevice, st));
+        d_in = ctx->in_stage.as<uint8_t>();
+        if (n >= 2) memcpy(hdr, in, 2);
+    } else if (has_header && n >= 2) {
+        CU(cudaMemcpyAsync(hdr, d_in, 2, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (has_header) {
+        if (n < 2) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+        if ((hdr[0] & 0xf) != 8) return fail(ctx, ZSB_DATA_ERROR, "unknown compression method");
+        if ((hdr[0] >> 4) + 8 > 15) return fail(ctx, ZSB_DATA_ERROR, "invalid window size");
+        if ((((unsigned)hdr[0] << 8) + hdr[1]) % 31 != 0) return fail(ctx, ZSB_DATA_ERROR, "incorrect header check");
+        if (hdr[1] & 0x20) return fail(ctx, ZSB_NEED_DICT, "need dictionary");
+    }
+    const uint64_t* d_seg_end = seg_end_offsets;
+    std::vector<uint64_t> host_ends;
+    if (!(flags & ZSB_OFFSETS_DEVICE)) {
+        CU(ctx->seg_end.reserve((nseg ? nseg : 1) * sizeof(uint64_t)));
+        CU(cudaMemcpyAsync(ctx->seg_end.p, seg_end_offsets, nseg * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        d_seg_end = ctx->seg_end.as<uint64_t>();
+    }
+    uint64_t last_end = has_header ? 2 : 0;
+    if (nseg) {
+        if (flags & ZSB_OFFSETS_DEVICE) {
+            CU(cudaMemcpyAsync(&last_end, seg_end_offsets + (nseg - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        } else last_end = seg_end_offsets[nseg - 1];
+    }
+    if (last_end + (has_trailer ? 6 : 0) > n) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+
+    uint8_t* d_out = reinterpret_cast<uint8_t*>(out);
+    if (!(flags & ZSB_OUT_DEVICE)) {
+        CU(ctx->out_stage.reserve(out_cap ? out_cap : 1));
+        d_out = ctx->out_stage.as<uint8_t>();
+    }
+    CU(ctx->inf_len.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
+    CU(ctx->inf_status.reserve((nseg ? nseg : 1) * sizeof(int)));
+    const size_t total_out = out_cap < nseg * seg_size ? out_cap : nseg * seg_size;
+    const size_t achunks = (total_out + kAdlerChunk - 1) / kAdlerChunk;
+    CU(ctx->seg_adler.reserve((achunks ? achunks : 1) * sizeof(uint2)));
+
+    uint8_t* small = ctx->small.as<uint8_t>();
+    uint32_t* d_adler = reinterpret_cast<uint32_t*>(small + 12);
+    unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
+    CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+
+    InflateParams I;
+    I.in = d_in;
+    I.n = n;
+    I.seg_end = d_seg_end;
+    I.first_offset = has_header ? 2 : 0;
+    I.nseg = (uint32_t)nseg;
+    I.seg_size = (uint32_t)seg_size;
+    I.out = d_out;
+    I.out_cap = total_out;
+    I.seg_out_len = ctx->inf_len.as<uint32_t>();
+    I.seg_adler = nullptr;
+    I.seg_status = ctx->inf_status.as<int>();
+    I.work_counter = d_work;
+    timing_mark(ctx, 2, true);
+    CU(launch_inflate(I, ctx->num_sms, st));
+    timing_mark(ctx, 2, false);
+    ctx->launches++;
+    std::vector<int> status(nseg);
+    std::vector<uint32_t> lens(nseg);
+    uint32_t got_adler = 1;
+    uint8_t trailer[6] = {0};
+    if (nseg) {
+        CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (has_trailer) CU(cudaMemcpyAsync(trailer, d_in + last_end, 6, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    size_t produced = 0;
+    for (size_t k = 0; k < nseg; k++) {
+        if (status[k] != IE_OK) {
+            int e = status[k];
+            if (e < 0 || e > IE_SEG_SIZE) e = IE_TRUNCATED;
+            char buf[160];
+            snprintf(buf, sizeof buf, "%s (segment %zu)", kInflateMsg[e], k);
+            // the reference reports only the message; the segment index is appended for the batch caller
+            return fail(ctx, (e == IE_TRUNCATED || e == IE_OUTPUT_OVERFLOW) ? ZSB_BUF_ERROR : ZSB_DATA_ERROR, buf);
+        }
+        produced += lens[k];
+    }
+    if (out_len) *out_len = produced;
+    // running Adler-32 of the output (InflateBlocks.cs:755,792) as a separate pass over the decoded bytes
+    CU(launch_adler32(d_out, produced, 1u, ctx->seg_adler.as<uint2>(), (uint32_t)(achunks ? achunks : 1), d_adler, st));
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(&got_adler, d_adler, sizeof got_adler, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (adler) *adler = got_adler;
+    if (has_trailer) {
+        // final block must be the empty static block `03 00` (Q12) followed by the big-endian Adler-32
+        if (trailer[0] != 0x03 || trailer[1] != 0x00) return fail(ctx, ZSB_DATA_ERROR, "invalid block type");
+        const uint32_t want = ((uint32_t)trailer[2] << 24) | ((uint32_t)trailer[3] << 16) | ((uint32_t)trailer[4] << 8) | trailer[5];
+        if (want != got_adler) return fail(ctx, ZSB_DATA_ERROR, "incorrect data check");  // Inflate.cs:335-342
+    }
+    if (!(flags & ZSB_OUT_DEVICE) && produced) {
+        CU(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return has_trailer ? ZSB_STREAM_END : ZSB_OK;
+}
+
+int zsb_adler32(zsb_ctx* ctx, uint32_t seed, const void* p, size_t n, unsigned flags, uint32_t* result)
+{
+    if (!ctx || !result) return ZSB_STREAM_ERROR;
+    ctx->err.clear();
+    if (n == 0) { *result = seed; return ZSB_OK; }  // Adler32.cs:63-66
+    if (!p) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint8_t* d_p = reinterpret_cast<const uint8_t*>(p);
+    if (!(flags & ZSB_IN_DEVICE)) {
+        CU(ctx->in_stage.reserve(n));
+        CU(cudaMemcpyAsync(ctx->in_stage.p, p, n, cudaMemcpyHostToDevice, st));
+        d_p = ctx->in_stage.as<uint8_t>();
+    }
+    const size_t chunks = (n + kAdlerChunk - 1) / kAdlerChunk;
+    if (chunks > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "input too large");
+    CU(ctx->seg_adler.reserve(chunks * sizeof(uint2)));
+    uint32_t* d_adler = reinterpret_cast<uint32_t*>(ctx->small.as<uint8_t>() + 12);
+    CU(launch_adler32(d_p, n, seed, ctx->seg_adler.as<uint2>(), (uint32_t)chunks, d_adler, st));
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(result, d_adler, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ZSB_OK;
+}
+
+uint32_t zsb_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2)
+{
+    const uint32_t BASE = 65521u;
+    const uint32_t rem = (uint32_t)(len2 % BASE);
+    uint64_t s1 = (uint64_t)(a1 & 0xFFFF) + (a2 & 0xFFFF) + BASE - 1;
+    uint64_t s2 = (uint64_t)(a1 >> 16) + (a2 >> 16) + (uint64_t)rem * (((a1 & 0xFFFF) + BASE - 1) % BASE);
+    return (uint32_t)(s1 % BASE) | ((uint32_t)(s2 % BASE) << 16);
+}
+
+}  // extern "C"
+
+// ---- diagnostics (tests only): raw copies of the last deflate batch's intermediate buffers -----------------
+extern "C" ZSB_API int zsb_debug_fetch(zsb_ctx* ctx, int what, uint64_t byte_offset, void* dst, size_t bytes)
+{
+    if (!ctx || !dst) return ZSB_STREAM_ERROR;
+    const DevBuf* b = nullptr;
+    switch (what) {
+        case 0: b = &ctx->sym; break;        // uint32 dist | lc << 16, [seg][seg_size]
+        case 1: b = &ctx->blocks; break;     // BlockRec [seg][max_blocks]
+        case 2: b = &ctx->nblocks; break;    // uint32 [seg]
+        case 3: b = &ctx->layout; break;     // SegLayout [seg]
+        case 4: b = &ctx->codes; break;      // BlockCodesDev [seg][max_blocks]
+        case 5: b = &ctx->seg_adler; break;  // uint2 [seg]
+        default: return ZSB_STREAM_ERROR;
+    }
+    if (byte_offset + bytes > b->cap) return fail(ctx, ZSB_BUF_ERROR, "debug fetch out of range");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(dst, reinterpret_cast<const uint8_t*>(b->p) + byte_offset, bytes, cudaMemcpyDeviceToHost));
+    return ZSB_OK;
+}

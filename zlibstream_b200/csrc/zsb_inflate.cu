@@ -1,0 +1,363 @@
+// zsb_inflate.cu -- inflate of full-flush-segmented deflate streams: one warp per segment.
+//
+// Replaces Inflate.Decompress (Inflate.cs:103-357, block loop), InflateBlocks.Process
+// (InflateBlocks.cs:130-713), InfCodes.Inflate_fast / Process (InfCodes.cs:106-817) and
+// InfTree.Huft_build (InfTree.cs:125-365; RFC 1951 semantics, not the reference's broken table copy,
+// SURVEY Q15).  A full-flush segment starts byte aligned with an empty history (Deflate.cs:596-605), so
+// segments decode independently; the per-warp state is two lookup tables in shared memory, output goes
+// straight to HBM and back-references are served from L2.
+#include "zsb_kernels.cuh"
+
+namespace zsb {
+
+namespace {
+
+constexpr int INF_WARPS = 8;
+constexpr int INF_THREADS = INF_WARPS * 32;
+constexpr int FAST_L = 10;   // root table bits, literal/length
+constexpr int FAST_D = 8;    // root table bits, distance
+
+struct WarpTables {
+    uint16_t fast_l[1 << FAST_L];   // (sym << 4) | len, 0 = longer than FAST_L bits
+    uint16_t fast_d[1 << FAST_D];
+    uint16_t sorted_l[288];
+    uint16_t sorted_d[32];
+    uint16_t count_l[16], first_l[16], offset_l[16];
+    uint16_t count_d[16], first_d[16], offset_d[16];
+    uint16_t code_tmp[320];
+    uint8_t lens[352];
+};
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct BitReader {   // lane 0 only
+    const uint8_t* in;
+    uint64_t pos, end;   // byte offsets inside `in`
+    uint64_t acc;
+    int nbits;
+    __device__ __forceinline__ void refill()
+    {
+        while (nbits <= 56 && pos < end) {
+            acc |= (uint64_t)in[pos++] << nbits;
+            nbits += 8;
+        }
+    }
+    __device__ __forceinline__ bool need(int k)
+    {
+        if (nbits < k) refill();
+        return nbits >= k;
+    }
+    __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)(acc & ((1ull << k) - 1)); }
+    __device__ __forceinline__ void drop(int k) { acc >>= k; nbits -= k; }
+    __device__ __forceinline__ uint64_t byte_pos() const { return pos - (uint64_t)(nbits >> 3); }
+};
+
+// Builds one canonical decoding table from sm.lens[base .. base+n).  Whole warp.
+// Returns 0 ok, 1 all zero, -1 oversubscribed, -2 incomplete (InfTree.cs huft_build rules).
+__device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane)
+{
+    uint16_t* fast = dist ? t.fast_d : t.fast_l;
+    uint16_t* sorted = dist ? t.sorted_d : t.sorted_l;
+    uint16_t* count = dist ? t.count_d : t.count_l;
+    uint16_t* first = dist ? t.first_d : t.first_l;
+    uint16_t* offset = dist ? t.offset_d : t.offset_l;
+    const int fast_bits = dist ? FAST_D : FAST_L;
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    int rc = 0;
+    if (lane == 0) {
+        for (int i = 0; i < 16; i++) count[i] = 0;
+        for (int i = 0; i < n; i++) count[t.lens[base + i]]++;
+        if (count[0] == n) rc = 1;
+        else {
+            int left = 1, maxlen = 0;
+            for (int len = 1; len <= MAX_BITS; len++) {
+                left <<= 1;
+                left -= count[len];
+                if (left < 0) { rc = -1; break; }
+                if (count[len]) maxlen = len;
+            }
+            if (rc == 0) {
+                count[0] = 0;
+                uint32_t code = 0;
+                offset[1] = 0;
+                uint16_t next_off[16], next_code[16];
+                for (int len = 1; len <= MAX_BITS; len++) {
+                    code = (code + count[len - 1]) << 1;
+                    first[len] = (uint16_t)code;
+                    next_code[len] = (uint16_t)code;
+                    if (len < MAX_BITS) offset[len + 1] = (uint16_t)(offset[len] + count[len]);
+                }
+                for (int len = 1; len <= MAX_BITS; len++) next_off[len] = offset[len];
+                for (int i = 0; i < n; i++) {
+                    int len = t.lens[base + i];
+                    if (len) {
+                        sorted[next_off[len]++] = (uint16_t)i;
+                        t.code_tmp[i] = next_code[len]++;
+                    }
+                }
+                if (left > 0 && maxlen != 1) rc = -2;
+            }
+        }
+    }
+    rc = __shfl_sync(0xffffffffu, rc, 0);
+    __syncwarp();
+    if (rc == 0 || rc == -2) {
+        for (int i = lane; i < n; i += 32) {
+            const int len = t.lens[base + i];
+            if (len && len <= fast_bits) {
+                const uint32_t r = __brev((uint32_t)t.code_tmp[i]) >> (32 - len);
+                for (uint32_t k = r; k < (1u << fast_bits); k += 1u << len) fast[k] = (uint16_t)((i << 4) | len);
+            }
+        }
+    }
+    __syncwarp();
+    return rc;
+}
+
+// lane 0: decode one symbol. >= 0 symbol, -1 invalid code, -2 out of input
+__device__ __forceinline__ int decode_sym(BitReader& b, const uint16_t* fast, int fast_bits, const uint16_t* count,
+                                          const uint16_t* first, const uint16_t* offset, const uint16_t* sorted)
+{
+    b.refill();
+    const uint32_t e = fast[b.acc & ((1u << fast_bits) - 1)];
+    if (e) {
+        const int len = (int)(e & 15);
+        if (len > b.nbits) return -2;
+        b.drop(len);
+        return (int)(e >> 4);
+    }
+    uint32_t code = 0;
+    uint64_t acc = b.acc;
+    for (int len = 1; len <= MAX_BITS; len++) {
+        if (len > b.nbits) return -2;
+        code = (code << 1) | (uint32_t)(acc & 1);
+        acc >>= 1;
+        const uint32_t cnt = count[len];
+        if (cnt && code >= first[len] && code - first[len] < cnt) {
+            b.drop(len);
+            return sorted[offset[len] + (code - first[len])];
+        }
+    }
+    return -1;
+}
+
+enum { OP_LIT = 0, OP_MATCH = 1, OP_EOB = 2, OP_ERR = 3 };
+
+}  // namespace
+
+__global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflateParams P)
+{
+    __shared__ WarpTables tabs[INF_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpTables& t = tabs[warp];
+
+    for (;;) {
+        uint32_t seg = 0;
+        if (lane == 0) seg = atomicAdd(P.work_counter, 1u);
+        seg = __shfl_sync(0xffffffffu, seg, 0);
+        if (seg >= P.nseg) break;
+
+        const uint64_t c_begin = seg == 0 ? P.first_offset : P.seg_end[seg - 1];
+        const uint64_t c_end = P.seg_end[seg];
+        const uint64_t o_begin = (uint64_t)seg * P.seg_size;
+        const uint64_t o_cap = (P.out_cap - o_begin) < P.seg_size ? (P.out_cap - o_begin) : P.seg_size;
+        uint8_t* out = P.out + o_begin;
+        uint64_t o = 0;
+        int err = IE_OK;
+        BitReader br;
+        br.in = P.in;
+        br.pos = c_begin;
+        br.end = c_end < P.n ? c_end : P.n;
+        br.acc = 0;
+        br.nbits = 0;
+        if (c_end > P.n || c_begin > c_end) err = IE_TRUNCATED;
+
+        // blocks until the segment's compressed bytes are used up (it ends with the full-flush marker)
+        while (err == IE_OK) {
+            int hdr = -1;
+            if (lane == 0) {
+                if (br.byte_pos() >= br.end && br.nbits < 8) hdr = -2;       // clean end of segment
+                else if (!br.need(3)) hdr = -3;
+                else { hdr = (int)br.peek(3); br.drop(3); }
+            }
+            hdr = __shfl_sync(0xffffffffu, hdr, 0);
+            if (hdr == -2) break;
+            if (hdr == -3) { err = IE_TRUNCATED; break; }
+            const int type = hdr >> 1;   // BFINAL is ignored inside a segment: the stream's final block is the caller's
+            if (type == 0) {
+                // stored (InflateBlocks.cs:251-364)
+                int len = -1;
+                if (lane == 0) {
+                    br.drop(br.nbits & 7);
+                    if (br.need(32)) {
+                        const uint32_t l = br.peek(16);
+                        br.drop(16);
+                        const uint32_t nl = br.peek(16);
+                        br.drop(16);
+                        len = (((~nl) & 0xFFFF) == l) ? (int)l : -2;
+                    }
+                }
+                len = __shfl_sync(0xffffffffu, len, 0);
+                if (len == -1) { err = IE_TRUNCATED; break; }
+                if (len == -2) { err = IE_STORED_LEN; break; }
+                uint64_t src = 0;
+                if (lane == 0) src = br.byte_pos();
+                src = __shfl_sync(0xffffffffu, src, 0);
+                if (src + (uint64_t)len > br.end) { err = IE_TRUNCATED; break; }
+                if (o + (uint64_t)len > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
+                for (int i = lane; i < len; i += 32) out[o + i] = P.in[src + i];
+                o += (uint64_t)len;
+                if (lane == 0) { br.pos = src + (uint64_t)len; br.acc = 0; br.nbits = 0; }
+                __syncwarp();
+                continue;
+            }
+            if (type == 3) { err = IE_BLOCK_TYPE; break; }
+            if (type == 1) {
+                // fixed tables (InfTree.cs:16-96)
+                for (int i = lane; i < 288; i += 32) t.lens[i] = (uint8_t)static_llen(i);
+                for (int i = lane; i < 30; i += 32) t.lens[288 + i] = 5;
+                __syncwarp();
+                build_table(t, 0, 288, false, lane);
+                build_table(t, 288, 30, true, lane);
+            } else {
+                // dynamic header (InflateBlocks.cs:366-626)
+                int nl = 0, nd = 0, e = IE_OK;
+                if (lane == 0) {
+                    if (!br.need(14)) e = IE_TRUNCATED;
+                    else {
+                        const uint32_t v = br.peek(14);
+                        br.drop(14);
+                        if ((v & 0x1f) > 29 || ((v >> 5) & 0x1f) > 29) e = IE_TOO_MANY_SYMS;
+                        else {
+                            nl = 257 + (int)(v & 0x1f);
+                            nd = 1 + (int)((v >> 5) & 0x1f);
+                            const int nb = 4 + (int)(v >> 10);
+                            for (int i = 0; i < 19; i++) t.lens[i] = 0;
+                            for (int i = 0; i < nb && e == IE_OK; i++) {
+                                if (!br.need(3)) e = IE_TRUNCATED;
+                                else { t.lens[c_order[i]] = (uint8_t)br.peek(3); br.drop(3); }
+                            }
+                        }
+                    }
+                }
+                e = __shfl_sync(0xffffffffu, e, 0);
+                if (e != IE_OK) { err = e; break; }
+                nl = __shfl_sync(0xffffffffu, nl, 0);
+                nd = __shfl_sync(0xffffffffu, nd, 0);
+                __syncwarp();
+                // the bit-length code is decoded through the distance-table slots
+                int r = build_table(t, 0, 19, true, lane);
+                if (r == -1) { err = IE_OVERSUB_BL; break; }
+                if (r != 0) { err = IE_INCOMPLETE_BL; break; }
+                if (lane == 0) {
+                    int i = 0;
+                    uint8_t prev = 0;
+                    while (i < nl + nd && e == IE_OK) {
+                        const int sym = decode_sym(br, t.fast_d, FAST_D, t.count_d, t.first_d, t.offset_d, t.sorted_d);
+                        if (sym == -2) e = IE_TRUNCATED;
+                        else if (sym < 0) e = IE_BAD_REPEAT;
+                        else if (sym < 16) { t.lens[32 + i++] = prev = (uint8_t)sym; }
+                        else {
+                            const int eb = sym == 18 ? 7 : sym - 14, rb = sym == 18 ? 11 : 3;
+                            if (!br.need(eb)) { e = IE_TRUNCATED; break; }
+                            int rep = rb + (int)br.peek(eb);
+                            br.drop(eb);
+                            if (i + rep > nl + nd || (sym == 16 && i < 1)) { e = IE_BAD_REPEAT; break; }
+                            const uint8_t v = sym == 16 ? prev : 0;
+                            if (sym != 16) prev = 0;
+                            while (rep--) t.lens[32 + i++] = v;
+                        }
+                    }
+                }
+                e = __shfl_sync(0xffffffffu, e, 0);
+                if (e != IE_OK) { err = e; break; }
+                __syncwarp();
+                r = build_table(t, 32, nl, false, lane);
+                if (r == -1) { err = IE_OVERSUB_L; break; }
+                if (r != 0) { err = IE_INCOMPLETE_L; break; }
+                r = build_table(t, 32 + nl, nd, true, lane);
+                if (r == -1) { err = IE_OVERSUB_D; break; }
+                if (r == -2) { err = IE_INCOMPLETE_D; break; }
+                if (r == 1 && nl > 257) { err = IE_EMPTY_D; break; }
+            }
+            // ---- symbols (InfCodes.cs:106-817): lane 0 decodes, the warp copies matches ----
+            for (;;) {
+                int op = OP_ERR, a = 0, d = 0;
+                if (lane == 0) {
+                    const int sym = decode_sym(br, t.fast_l, FAST_L, t.count_l, t.first_l, t.offset_l, t.sorted_l);
+                    if (sym == -2) { a = IE_TRUNCATED; }
+                    else if (sym < 0) { a = IE_BAD_LCODE; }
+                    else if (sym < 256) { op = OP_LIT; a = sym; }
+                    else if (sym == 256) { op = OP_EOB; }
+                    else if (sym - 257 >= 29) { a = IE_BAD_LCODE; }
+                    else {
+                        const int ls = sym - 257;
+                        int eb = c_len_extra[ls];
+                        if (!br.need(eb)) a = IE_TRUNCATED;
+                        else {
+                            const int len = c_len_base[ls] + (int)br.peek(eb);
+                            br.drop(eb);
+                            const int ds = decode_sym(br, t.fast_d, FAST_D, t.count_d, t.first_d, t.offset_d, t.sorted_d);
+                            if (ds == -2) a = IE_TRUNCATED;
+                            else if (ds < 0 || ds >= 30) a = IE_BAD_DCODE;
+                            else {
+                                eb = c_dist_extra[ds];
+                                if (!br.need(eb)) a = IE_TRUNCATED;
+                                else {
+                                    d = c_dist_base[ds] + (int)br.peek(eb);
+                                    br.drop(eb);
+                                    a = len;
+                                    op = OP_MATCH;
+                                }
+                            }
+                        }
+                    }
+                    if (op == OP_LIT) {
+                        if (o < o_cap) out[o] = (uint8_t)a;
+                        else { op = OP_ERR; a = IE_OUTPUT_OVERFLOW; }
+                    }
+                }
+                op = __shfl_sync(0xffffffffu, op, 0);
+                if (op == OP_LIT) { o++; continue; }
+                if (op == OP_EOB) break;
+                a = __shfl_sync(0xffffffffu, a, 0);
+                if (op == OP_ERR) { err = a; break; }
+                d = __shfl_sync(0xffffffffu, d, 0);
+                if ((uint64_t)d > o) { err = IE_DIST_TOO_FAR; break; }
+                if (o + (uint64_t)a > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
+                __syncwarp();
+                // out[o + i] = out[o - d + (i mod d)]: every source byte was written before this match
+                for (int i = lane; i < a; i += 32) {
+                    const int k = i < d ? i : i % d;
+                    out[o + i] = __ldcg(out + o - d + k);
+                }
+                o += (uint64_t)a;
+                __syncwarp();
+            }
+            if (err != IE_OK) break;
+        }
+        // every segment but the last holds exactly seg_size bytes (that is what places the output)
+        if (err == IE_OK && seg + 1 < P.nseg && o != P.seg_size) err = IE_SEG_SIZE;
+        if (lane == 0) {
+            P.seg_out_len[seg] = (uint32_t)o;
+            P.seg_status[seg] = err;
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream)
+{
+    if (P.nseg == 0) return cudaSuccess;
+    int ctas = num_sms * 4;
+    const int need = (int)((P.nseg + INF_WARPS - 1) / INF_WARPS);
+    if (ctas > need) ctas = need;
+    inflate_segments_kernel<<<ctas, INF_THREADS, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace zsb

@@ -1,0 +1,108 @@
+// zsb_kernels.cuh -- kernel parameter blocks and host-side launchers shared by the .cu files.
+#pragma once
+
+#include "zsb_common.cuh"
+
+namespace zsb {
+
+// ---- LZ77 (zsb_lz77.cu) ------------------------------------------------------------------------
+struct Lz77Params {
+    const uint8_t* in;        // first byte of the first segment handled by this launch
+    size_t n;                 // bytes from `in` to the end of the input
+    uint32_t seg_size;
+    uint32_t nseg;
+    uint64_t first_seg_index; // stream index of segment 0 of this launch
+    const uint8_t* halo;      // the 32768 bytes preceding `in` in the stream, or nullptr
+    int strategy, hash_variant;
+    int good, lazy, nice, chain, fn;
+    uint32_t* sym;            // [nseg][sym_stride]  dist | lc << 16
+    size_t sym_stride;
+    BlockRec* blocks;         // [nseg][max_blocks]
+    uint32_t max_blocks;
+    uint32_t* nblocks;        // [nseg]
+    uint2* seg_adler;         // [nseg] (s1, s2) of each segment, seed 1
+    unsigned int* work_counter;
+    const uint16_t* crc_tab;  // 4 * 256
+};
+size_t lz77_smem_bytes();
+cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream);
+
+// ---- Huffman stage (zsb_huffman.cu) --------------------------------------------------------------
+constexpr int kHdrWords = 80;   // dynamic tree description: <= 14 + 57 + 316 * 7 bits
+constexpr int kTailWords = 8;   // per-segment tail: empty static blocks and full-flush markers (Q10)
+
+struct BlockCodesDev {
+    uint32_t lcode[L_CODES];   // code | len << 16, code already bit-reversed
+    uint32_t dcode[D_CODES];
+    uint32_t hdr[kHdrWords];   // LSB-first bit string sent after the 3 block-type bits of a dynamic block
+};
+
+struct SegLayout {
+    uint64_t out_offset;   // byte offset of the segment's first output byte inside this call's output
+    uint32_t out_bytes;    // compressed size of the segment
+    uint32_t tail_nbits;
+    uint64_t tail_bit_offset;       // relative to the segment's first output bit
+    uint32_t tail[kTailWords];      // LSB-first bits
+};
+
+struct HuffParams {
+    const uint8_t* in;
+    size_t n;
+    uint32_t seg_size;
+    uint32_t nseg;
+    uint64_t first_seg_index;
+    int strategy;
+    const uint32_t* sym;
+    size_t sym_stride;
+    BlockRec* blocks;
+    uint32_t max_blocks;
+    const uint32_t* nblocks;
+    BlockCodesDev* codes;     // [nseg][max_blocks]
+    SegLayout* layout;        // [nseg]
+    uint64_t out_base;        // bytes already in `out` before the first segment of this launch (header, earlier batches)
+    uint64_t* total_out;      // device scalar: out offset after the last segment of this launch
+    uint64_t* seg_end;        // optional [nseg]: end offset of each segment inside `out`
+    uint8_t* out;
+    size_t out_cap;
+    int* status;              // device int: set to ZSB_BUF_ERROR if out_cap is too small
+};
+cudaError_t launch_block_trees(const HuffParams& P, cudaStream_t stream);
+cudaError_t launch_layout(const HuffParams& P, cudaStream_t stream);
+cudaError_t launch_pack(const HuffParams& P, cudaStream_t stream);
+
+// ---- Adler-32 (zsb_adler32.cu) -------------------------------------------------------------------
+// Folds per-segment (s1, s2) pairs (seed 1 each) into one checksum of the concatenation.
+cudaError_t launch_adler_fold(const uint2* seg_adler, uint32_t nseg, uint32_t seg_size, size_t n, uint32_t seed,
+                              uint32_t* result, cudaStream_t stream);
+// Stand-alone checksum: per-chunk partial sums + fold.
+cudaError_t launch_adler32(const uint8_t* p, size_t n, uint32_t seed, uint2* scratch, uint32_t scratch_len,
+                           uint32_t* result, cudaStream_t stream);
+constexpr uint32_t kAdlerChunk = 1u << 16;
+
+// ---- Inflate (zsb_inflate.cu) ---------------------------------------------------------------------
+struct InflateParams {
+    const uint8_t* in;
+    size_t n;                  // compressed bytes
+    const uint64_t* seg_end;   // [nseg] end offsets of each segment inside `in`
+    uint64_t first_offset;     // offset of the first segment's first byte (2 after a zlib header)
+    uint32_t nseg;
+    uint32_t seg_size;
+    uint8_t* out;
+    size_t out_cap;            // total uncompressed capacity
+    uint32_t* seg_out_len;     // [nseg] bytes produced per segment
+    uint2* seg_adler;          // [nseg]
+    int* seg_status;           // [nseg] 0 ok, else error id
+    unsigned int* work_counter;
+};
+cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream);
+// Scans `in` for full-flush markers and validates them into a segment index (device side).
+cudaError_t launch_index_markers(const uint8_t* in, size_t n, uint64_t first_offset, uint64_t* cand, uint32_t cand_cap,
+                                 uint32_t* ncand, cudaStream_t stream);
+
+enum InflateErr {
+    IE_OK = 0, IE_BLOCK_TYPE, IE_STORED_LEN, IE_TOO_MANY_SYMS, IE_BAD_REPEAT, IE_OVERSUB_BL, IE_INCOMPLETE_BL,
+    IE_OVERSUB_L, IE_INCOMPLETE_L, IE_OVERSUB_D, IE_INCOMPLETE_D, IE_EMPTY_D, IE_BAD_LCODE, IE_BAD_DCODE,
+    IE_DIST_TOO_FAR, IE_TRUNCATED, IE_OUTPUT_OVERFLOW, IE_SEG_SIZE
+};
+
+}  // namespace zsb

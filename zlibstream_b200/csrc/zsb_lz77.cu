@@ -1,0 +1,571 @@
+// zsb_lz77.cu -- LZ77 match finding for full-flush segments: one CTA per segment.
+//
+// Replaces Deflate.Fill_window / InsertString / Longest_match (Deflate.cs:866-1100), DeflateFast
+// (Deflate.Fast.cs:20-128), DeflateSlow (Deflate.Slow.cs:18-159), DeflateRle (Deflate.Rle.cs:18-104),
+// Compare256 / SlideHash / UpdateHash (Deflate.Intrinsics.cs) and Tr_tally_* (Deflate.cs:910-948).
+//
+// HBM layout: input is read once, 32 KiB at a time, straight into the shared-memory window with a bulk
+// async copy (TMA engine, cp.async.bulk + mbarrier); the 64 KiB window, head[32768] and prev[32768]
+// live in shared memory in the reference's own window coordinates (192 KiB per CTA, one CTA per SM),
+// so the refill / slide schedule -- which the output depends on -- is reproduced
+// literally.  Symbols (dist | lc << 16) are streamed to HBM; Adler-32 partial sums are taken from the
+// staged window so the checksum costs no extra HBM pass.
+#include "zsb_kernels.cuh"
+
+namespace zsb {
+
+namespace {
+
+constexpr int LZ_THREADS = 256;
+constexpr int WIN_PAD = 16;
+
+struct ParserState {
+    int str_start, lookahead, block_start, match_length, prev_length, match_start, prev_match, match_available;
+    int avail_in;      // bytes of the segment not yet read into the window
+    int in_pos;        // segment-relative offset of the next byte to read
+    int abs_base;      // segment-relative offset of window index 0
+    int last_lit;      // symbols in the open block
+    int sym_total;     // symbols emitted so far in this segment
+    int nblocks;
+    int done;
+};
+
+struct Smem {
+    uint8_t* win;    // WINDOW_SIZE + WIN_PAD
+    uint16_t* head;  // HASH_SIZE
+    uint16_t* prev;  // W_SIZE
+    uint16_t* crc;   // 4 * 256, low 16 bits of the slice-by-4 CRC-32C tables
+};
+
+__device__ __forceinline__ uint32_t hash_of(const Smem& sm, uint32_t v, int hash_variant)
+{
+    if (hash_variant == 0) {  // Sse42.Crc32(0, v): Deflate.Intrinsics.cs:298-301
+        uint32_t h = sm.crc[(v & 0xFF)] ^ sm.crc[256 + ((v >> 8) & 0xFF)] ^ sm.crc[512 + ((v >> 16) & 0xFF)] ^
+                     sm.crc[768 + (v >> 24)];
+        return h & HASH_MASK;
+    }
+    return ((v * 2654435761u) >> 16) & HASH_MASK;  // Deflate.Intrinsics.cs:305
+}
+
+// Deflate.cs:866-877 (Q1: hashes the 4 bytes at str+2; Q2: no update when head already == str)
+__device__ __forceinline__ int insert_string(const Smem& sm, int str, int hash_variant)
+{
+    uint32_t h = hash_of(sm, lds_u32_unaligned(sm.win, str + (MIN_MATCH - 1)), hash_variant);
+    int cur = sm.head[h];
+    if (cur != str) {
+        sm.prev[str & W_MASK] = (uint16_t)cur;
+        sm.head[h] = (uint16_t)str;
+    }
+    return cur;
+}
+
+// Compare256 (Deflate.Intrinsics.cs:19-162): common prefix length of two window strings, <= 256.
+__device__ __forceinline__ int compare256(const uint8_t* win, int a, int b)
+{
+    int len = 0;
+    while (len < 256) {
+        uint32_t x = lds_u32_unaligned(win, a + len) ^ lds_u32_unaligned(win, b + len);
+        if (x) return len + ((__ffs(x) - 1) >> 3);
+        len += 4;
+    }
+    return 256;
+}
+
+__device__ __forceinline__ uint32_t lds_u16_unaligned(const uint8_t* win, int idx)
+{
+    return lds_u32_unaligned(win, idx) & 0xFFFF;
+}
+
+// Deflate.cs:1022-1100
+__device__ int longest_match(const Smem& sm, ParserState& s, const LevelCfg& cfg, int cur_match)
+{
+    int chain_length = cfg.chain;
+    const int scan = s.str_start;
+    int best_len = s.prev_length;
+    const int limit = s.str_start > MAX_DIST ? s.str_start - MAX_DIST : 0;
+    int nice_match = cfg.nice;
+    int match_start = s.match_start;
+    if (best_len == 0) best_len = 1;
+    const uint32_t scan_start = lds_u16_unaligned(sm.win, scan);
+    uint32_t scan_end = lds_u16_unaligned(sm.win, scan + best_len - 1);
+    if (s.prev_length >= cfg.good) chain_length >>= 2;
+    if (nice_match > s.lookahead) nice_match = s.lookahead;
+    do {
+        if (cur_match >= s.str_start) break;
+        if (lds_u16_unaligned(sm.win, cur_match + best_len - 1) != scan_end ||
+            lds_u16_unaligned(sm.win, cur_match) != scan_start)
+            continue;
+        int len = compare256(sm.win, scan + 2, cur_match + 2) + 2;
+        if (len > best_len) {
+            match_start = cur_match;
+            best_len = len;
+            if (len >= nice_match) break;
+            scan_end = lds_u16_unaligned(sm.win, scan + best_len - 1);
+        }
+    } while ((cur_match = sm.prev[cur_match & W_MASK]) > limit && --chain_length != 0);
+    s.match_start = match_start;
+    return best_len < s.lookahead ? best_len : s.lookahead;
+}
+
+struct SegOut {
+    uint32_t* sym;
+    BlockRec* blocks;
+    int max_blocks;
+};
+
+// Flush_block_only (Deflate.cs:951-956) as far as the parser is concerned: close the block record.
+__device__ __forceinline__ void close_block(ParserState& s, const SegOut& o)
+{
+    if (s.nblocks < o.max_blocks) {
+        BlockRec& b = o.blocks[s.nblocks];
+        b.sym_begin = (uint32_t)(s.sym_total - s.last_lit);
+        b.sym_count = (uint32_t)s.last_lit;
+        b.in_begin = (uint32_t)(s.block_start + s.abs_base);
+        b.in_len = (uint32_t)(s.str_start - s.block_start);
+        b.buf_valid = s.block_start >= 0;
+    }
+    s.nblocks++;
+    s.last_lit = 0;
+    s.block_start = s.str_start;
+}
+
+// Both return the reference's `bflush`: the caller closes the block where the reference calls
+// Flush_block_only, i.e. after str_start has moved past the symbol.
+__device__ __forceinline__ bool tally_dist(ParserState& s, const SegOut& o, int dist, int lc)  // Deflate.cs:910-926
+{
+    o.sym[s.sym_total++] = (uint32_t)dist | ((uint32_t)lc << 16);
+    return ++s.last_lit == BLOCK_SYMS;
+}
+__device__ __forceinline__ bool tally_lit(ParserState& s, const SegOut& o, int c)  // Deflate.cs:935-948
+{
+    o.sym[s.sym_total++] = (uint32_t)c << 16;
+    return ++s.last_lit == BLOCK_SYMS;
+}
+
+// True when Fill_window (Deflate.cs:967-1019) would do something that needs the whole CTA.
+__device__ __forceinline__ bool fill_needed(const ParserState& s)
+{
+    return s.avail_in > 0 || s.str_start >= WINDOW_SIZE - MIN_LOOKAHEAD;
+}
+
+// Deflate.Fast.cs:20-128.  Runs until the window needs refilling / sliding or the segment is done.
+__device__ void parse_fast(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
+                           int hash_variant)
+{
+    for (;;) {
+        if (s.lookahead < MIN_LOOKAHEAD) {
+            if (fill_needed(s)) return;
+            if (s.lookahead == 0) break;
+        }
+        int hash_head = 0;
+        if (s.lookahead >= MIN_MATCH) hash_head = insert_string(sm, s.str_start, hash_variant);
+        if (hash_head != 0 && (s.str_start - hash_head) <= MAX_DIST) {
+            if (strategy != 2 /* HuffmanOnly */) s.match_length = longest_match(sm, s, cfg, hash_head);
+        }
+        bool bflush;
+        if (s.match_length >= MIN_MATCH) {
+            bflush = tally_dist(s, o, s.str_start - s.match_start, s.match_length - MIN_MATCH);
+            s.lookahead -= s.match_length;
+            if (s.match_length <= cfg.lazy && s.lookahead >= MIN_MATCH) {
+                s.match_length--;
+                do {
+                    s.str_start++;
+                    insert_string(sm, s.str_start, hash_variant);
+                } while (--s.match_length != 0);
+                s.str_start++;
+            } else {
+                s.str_start += s.match_length;
+                s.match_length = 0;
+            }
+        } else {
+            bflush = tally_lit(s, o, sm.win[s.str_start]);
+            s.lookahead--;
+            s.str_start++;
+        }
+        if (bflush) close_block(s, o);
+    }
+    close_block(s, o);  // the end-of-input Flush_block_only(false) (Deflate.Fast.cs:124)
+    s.done = 1;
+}
+
+// Deflate.Slow.cs:18-159
+__device__ void parse_slow(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
+                           int hash_variant)
+{
+    int hash_head = 0;  // Q8: stale value only matters when lookahead < 3, where it cannot change the output
+    for (;;) {
+        if (s.lookahead < MIN_LOOKAHEAD) {
+            if (fill_needed(s)) return;
+            if (s.lookahead == 0) break;
+        }
+        if (s.lookahead >= MIN_MATCH) hash_head = insert_string(sm, s.str_start, hash_variant);
+        s.prev_length = s.match_length;
+        s.prev_match = s.match_start;
+        s.match_length = MIN_MATCH - 1;
+        if (hash_head != 0 && s.prev_length < cfg.lazy && s.str_start - hash_head <= MAX_DIST) {
+            if (strategy != 2) s.match_length = longest_match(sm, s, cfg, hash_head);
+            if (s.match_length <= 5 &&
+                (strategy == 1 /* Filtered */ || (s.match_length == MIN_MATCH && s.str_start - s.match_start > 4096)))
+                s.match_length = MIN_MATCH - 1;
+        }
+        if (s.prev_length >= MIN_MATCH && s.match_length <= s.prev_length) {
+            const int max_insert = s.str_start + s.lookahead - MIN_MATCH;
+            const bool bflush = tally_dist(s, o, s.str_start - 1 - s.prev_match, s.prev_length - MIN_MATCH);
+            s.lookahead -= s.prev_length - 1;
+            s.prev_length -= 2;
+            do {
+                if (++s.str_start <= max_insert) hash_head = insert_string(sm, s.str_start, hash_variant);
+            } while (--s.prev_length != 0);
+            s.match_available = 0;
+            s.match_length = MIN_MATCH - 1;
+            s.str_start++;
+            if (bflush) close_block(s, o);
+        } else if (s.match_available != 0) {
+            if (tally_lit(s, o, sm.win[s.str_start - 1])) close_block(s, o);
+            s.str_start++;
+            s.lookahead--;
+        } else {
+            s.match_available = 1;
+            s.str_start++;
+            s.lookahead--;
+        }
+    }
+    if (s.match_available != 0) {
+        // `_ = Tr_tally_lit(...)`: the flush flag is ignored, the block is flushed right after anyway
+        o.sym[s.sym_total++] = (uint32_t)sm.win[s.str_start - 1] << 16;
+        s.last_lit++;
+        s.match_available = 0;
+    }
+    close_block(s, o);
+    s.done = 1;
+}
+
+// Deflate.Rle.cs:18-104
+__device__ void parse_rle(const Smem& sm, ParserState& s, const SegOut& o)
+{
+    for (;;) {
+        if (s.lookahead <= MAX_MATCH) {
+            if (fill_needed(s)) return;
+        }
+        if (s.lookahead == 0) break;
+        s.match_length = 0;
+        if (s.lookahead >= MIN_MATCH && s.str_start > 0) {  // Q14: window[strStart-1] may be the previous segment's last byte
+            int scan = s.str_start - 1;
+            const uint32_t prev = sm.win[scan];
+            if (prev == sm.win[scan + 1] && prev == sm.win[scan + 2] && prev == sm.win[scan + 3]) {
+                const int strend = s.str_start + MAX_MATCH;
+                scan += 3;
+                for (;;) {  // the reference's 8-way unrolled scan: stops at a mismatch or once scan >= strend
+                    int k;
+                    bool stop = false;
+                    for (k = 0; k < 8; k++) {
+                        if (prev != sm.win[++scan]) { stop = true; break; }
+                    }
+                    if (stop || !(scan < strend)) break;
+                }
+                s.match_length = MAX_MATCH - (strend - scan);
+                if (s.match_length > s.lookahead) s.match_length = s.lookahead;
+            }
+        }
+        bool bflush;
+        if (s.match_length >= MIN_MATCH) {
+            bflush = tally_dist(s, o, 1, s.match_length - MIN_MATCH);
+            s.lookahead -= s.match_length;
+            s.str_start += s.match_length;
+            s.match_length = 0;
+        } else {
+            bflush = tally_lit(s, o, sm.win[s.str_start]);
+            s.lookahead--;
+            s.str_start++;
+        }
+        if (bflush) close_block(s, o);
+    }
+    close_block(s, o);
+    s.done = 1;
+}
+
+// ---- bulk async copy (TMA engine) global -> shared -------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// Cooperative copy of n bytes global -> shared; uses the bulk-copy engine for the 16-byte aligned body.
+__device__ void stage_input(uint8_t* dst, const uint8_t* src, int n, uint64_t* bar, uint32_t& phase)
+{
+    const int tid = threadIdx.x;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    int body = aligned ? (n & ~15) : 0;
+    if (body > 0) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)body);
+            bulk_g2s(dst, src, (uint32_t)body, bar);
+        }
+    }
+    for (int i = body + tid; i < n; i += LZ_THREADS) dst[i] = src[i];
+    if (body > 0) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+    }
+}
+
+// Partial Adler sums of n staged bytes: s1 = sum b, s2 = sum (n - j) * b_j   (Adler32.cs:270-326 unrolled)
+__device__ void adler_chunk(const uint8_t* p, int n, uint32_t* red, uint32_t& a, uint32_t& b)
+{
+    const int tid = threadIdx.x;
+    unsigned long long s1 = 0, s2 = 0;
+    for (int i = tid * 4; i < n; i += LZ_THREADS * 4) {
+        if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(p + i) & 3) == 0)) {
+            uint32_t v = *reinterpret_cast<const uint32_t*>(p + i);
+            uint32_t b0 = v & 0xFF, b1 = (v >> 8) & 0xFF, b2 = (v >> 16) & 0xFF, b3 = v >> 24;
+            uint32_t t1 = b0 + b1 + b2 + b3;
+            uint32_t w = (uint32_t)(n - i);
+            s1 += t1;
+            s2 += (unsigned long long)w * t1 - (b1 + 2 * b2 + 3 * b3);
+        } else {
+            for (int j = i; j < n && j < i + 4; j++) {
+                s1 += p[j];
+                s2 += (unsigned long long)(n - j) * p[j];
+            }
+        }
+    }
+    // warp + block reduce
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, off);
+        s2 += __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    unsigned long long* r64 = reinterpret_cast<unsigned long long*>(red);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) {
+        r64[warp * 2] = s1;
+        r64[warp * 2 + 1] = s2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t1 = 0, t2 = 0;
+        for (int w = 0; w < LZ_THREADS / 32; w++) {
+            t1 += r64[w * 2];
+            t2 += r64[w * 2 + 1];
+        }
+        // running (a, b) over the segment: b += n * a_old + s2, a += s1  (mod 65521)
+        unsigned long long nb = (unsigned long long)b + (unsigned long long)(n % ADLER_BASE) * a + t2 % ADLER_BASE;
+        b = (uint32_t)(nb % ADLER_BASE);
+        a = (uint32_t)((a + t1) % ADLER_BASE);
+    }
+    __syncthreads();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params P)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem sm;
+    sm.win = smem_raw;
+    sm.head = reinterpret_cast<uint16_t*>(smem_raw + WINDOW_SIZE + WIN_PAD);
+    sm.prev = sm.head + HASH_SIZE;
+    sm.crc = sm.prev + W_SIZE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm.crc + 1024);
+    uint32_t* red = reinterpret_cast<uint32_t*>(bar + 1);  // 2 * 8 * u64
+    ParserState* shared_state = reinterpret_cast<ParserState*>(red + 64);
+    int* seg_slot = reinterpret_cast<int*>(shared_state + 1);
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 1024; i += LZ_THREADS) sm.crc[i] = P.crc_tab[i];
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+
+    LevelCfg cfg;
+    cfg.good = P.good; cfg.lazy = P.lazy; cfg.nice = P.nice; cfg.chain = P.chain; cfg.fn = P.fn;
+
+    for (;;) {
+        if (tid == 0) *seg_slot = (int)atomicAdd(P.work_counter, 1u);
+        __syncthreads();
+        const int seg = *seg_slot;
+        __syncthreads();
+        if (seg >= (int)P.nseg) break;
+
+        const size_t seg_off = (size_t)seg * P.seg_size;
+        const int seg_len = (int)((P.n - seg_off) < (size_t)P.seg_size ? (P.n - seg_off) : (size_t)P.seg_size);
+        const uint8_t* seg_in = P.in + seg_off;
+        const bool stream_first = (P.first_seg_index + (uint64_t)seg) == 0;
+
+        // ---- per-segment init: head zeroed by the previous full flush (Deflate.cs:596-605) ----
+        {
+            uint4 z = make_uint4(0, 0, 0, 0);
+            uint4* h4 = reinterpret_cast<uint4*>(sm.head);
+            for (int i = tid; i < HASH_SIZE * 2 / 16; i += LZ_THREADS) h4[i] = z;
+            if (stream_first) {  // a freshly rented window is zero-filled (Q7)
+                uint4* w4 = reinterpret_cast<uint4*>(sm.win);
+                for (int i = tid; i < (WINDOW_SIZE + WIN_PAD) / 16; i += LZ_THREADS) w4[i] = z;
+            } else {
+                // Window as the previous segment left it (Q4): both halves hold its last 32 KiB.  Only two
+                // things can observe that: Rle through window[32767] (Q14) and stale bytes past a short
+                // final segment (Q7).
+                const uint8_t* before = nullptr;  // the 32768 bytes preceding this segment in the stream
+                if (seg > 0) before = seg_in - W_SIZE;
+                else if (P.halo) before = P.halo;
+                if (before && seg_len < W_SIZE + MIN_LOOKAHEAD) {
+                    for (int i = tid; i < W_SIZE; i += LZ_THREADS) {
+                        uint8_t v = before[i];
+                        sm.win[i] = v;
+                        sm.win[W_SIZE + i] = v;
+                    }
+                } else if (!before && seg_len < W_SIZE + MIN_LOOKAHEAD) {
+                    // no halo supplied: deterministic (zero) history instead of the reference's stale bytes
+                    for (int i = tid; i < WINDOW_SIZE; i += LZ_THREADS) sm.win[i] = 0;
+                } else if (tid == 0) {
+                    sm.win[W_SIZE - 1] = before ? before[W_SIZE - 1] : 0;
+                }
+                for (int i = tid; i < WIN_PAD; i += LZ_THREADS) sm.win[WINDOW_SIZE + i] = 0;
+            }
+        }
+        uint32_t adler_a = 1, adler_b = 0;
+        if (tid == 0) {
+            ParserState s;
+            s.str_start = stream_first ? 0 : W_SIZE;
+            s.block_start = s.str_start;
+            s.abs_base = stream_first ? 0 : -W_SIZE;
+            s.lookahead = 0;
+            s.match_length = s.prev_length = MIN_MATCH - 1;
+            s.match_start = 0;
+            s.prev_match = 0;
+            s.match_available = 0;
+            s.avail_in = seg_len;
+            s.in_pos = 0;
+            s.last_lit = 0;
+            s.sym_total = 0;
+            s.nblocks = 0;
+            s.done = 0;
+            *shared_state = s;
+        }
+        __syncthreads();
+
+        SegOut o;
+        o.sym = P.sym + (size_t)seg * P.sym_stride;
+        o.blocks = P.blocks + (size_t)seg * P.max_blocks;
+        o.max_blocks = (int)P.max_blocks;
+
+        for (;;) {
+            // ---- Fill_window (Deflate.cs:967-1019), executed by the whole CTA ----
+            {
+                int str_start = shared_state->str_start, lookahead = shared_state->lookahead;
+                int avail_in = shared_state->avail_in, in_pos = shared_state->in_pos;
+                const int thresh = (cfg.fn == FN_RLE) ? MAX_MATCH + 1 : MIN_LOOKAHEAD;
+                __syncthreads();
+                if (lookahead < thresh) {
+                    do {
+                        int more = WINDOW_SIZE - lookahead - str_start;
+                        if (str_start >= WINDOW_SIZE - MIN_LOOKAHEAD) {
+                            // slide: window memcpy + SlideHash (Deflate.Intrinsics.cs:261-285)
+                            {
+                                const uint4* src = reinterpret_cast<const uint4*>(sm.win + W_SIZE);
+                                uint4* dst = reinterpret_cast<uint4*>(sm.win);
+                                for (int i = tid; i < W_SIZE / 16; i += LZ_THREADS) dst[i] = src[i];
+                                uint32_t* hp = reinterpret_cast<uint32_t*>(sm.head);  // head and prev are contiguous
+                                for (int i = tid; i < (HASH_SIZE + W_SIZE) / 2; i += LZ_THREADS) {
+                                    uint32_t v = hp[i];
+                                    uint32_t lo = v & 0xFFFF, hi = v >> 16;
+                                    lo = lo >= W_SIZE ? lo - W_SIZE : 0;
+                                    hi = hi >= W_SIZE ? hi - W_SIZE : 0;
+                                    hp[i] = lo | (hi << 16);
+                                }
+                            }
+                            str_start -= W_SIZE;
+                            if (tid == 0) {
+                                shared_state->match_start -= W_SIZE;
+                                shared_state->block_start -= W_SIZE;
+                                shared_state->abs_base += W_SIZE;
+                            }
+                            more += W_SIZE;
+                            __syncthreads();
+                        }
+                        if (avail_in == 0) break;
+                        int n = avail_in < more ? avail_in : more;
+                        stage_input(sm.win + str_start + lookahead, seg_in + in_pos, n, bar, phase);
+                        __syncthreads();
+                        adler_chunk(sm.win + str_start + lookahead, n, red, adler_a, adler_b);
+                        avail_in -= n;
+                        in_pos += n;
+                        lookahead += n;
+                        // Q3: every refill inserts string str_start + 1
+                        if (tid == 0 && lookahead >= MIN_MATCH) insert_string(sm, str_start + 1, P.hash_variant);
+                        __syncthreads();
+                    } while (lookahead < MIN_LOOKAHEAD && avail_in != 0);
+                    if (tid == 0) {
+                        shared_state->str_start = str_start;
+                        shared_state->lookahead = lookahead;
+                        shared_state->avail_in = avail_in;
+                        shared_state->in_pos = in_pos;
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- parse until the next refill / slide or the end of the segment ----
+            if (tid == 0) {
+                ParserState s = *shared_state;
+                if (cfg.fn == FN_FAST) parse_fast(sm, s, o, cfg, P.strategy, P.hash_variant);
+                else if (cfg.fn == FN_SLOW) parse_slow(sm, s, o, cfg, P.strategy, P.hash_variant);
+                else parse_rle(sm, s, o);
+                *shared_state = s;
+            }
+            __syncthreads();
+            if (shared_state->done) break;
+        }
+        if (tid == 0) {
+            P.nblocks[seg] = (uint32_t)shared_state->nblocks;
+            P.seg_adler[seg] = make_uint2(adler_a, adler_b);
+        }
+        __syncthreads();
+    }
+}
+
+size_t lz77_smem_bytes()
+{
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16;
+}
+
+cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
+{
+    static bool configured = false;
+    size_t smem = lz77_smem_bytes();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lz77_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int grid = (int)(P.nseg < (uint32_t)num_sms ? P.nseg : (uint32_t)num_sms);
+    if (grid < 1) grid = 1;
+    lz77_segments_kernel<<<grid, LZ_THREADS, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace zsb

@@ -1,0 +1,183 @@
+"""GPU parity: libzsb200's segmented deflate must be bit-identical to the oracle (= the reference's dialect) for the
+same level / strategy / hash variant / full-flush segment boundaries.  All calls go through the C ABI."""
+import hashlib
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus_data
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEGMENTED = json.load(open(os.path.join(HERE, "golden", "segmented.json")))
+
+
+def _blob(corpus):
+    return b"".join(corpus[k] for k in sorted(corpus))
+
+
+@pytest.mark.parametrize("key", sorted(SEGMENTED))
+def test_golden_segmented_vectors(engine, corpus, key):
+    """Committed oracle outputs (tests/golden/segmented.json): L1/3/6/9, Filtered, HuffmanOnly, Rle, Fixed; 64 / 256 KiB."""
+    _, seg, lvl, strat = key.split("/")
+    ss, level, strategy = int(seg[3:]), int(lvl[1:]), int(strat[1:])
+    data = _blob(corpus)
+    got, ends, adler = engine.deflate_segments(data, ss, level, strategy)
+    g = SEGMENTED[key]
+    assert len(got) == g["len"] and hashlib.sha256(got).hexdigest() == g["sha256"]
+    assert adler == g["adler"] == zlib.adler32(data)
+    assert hashlib.sha256(",".join(map(str, ends)).encode()).hexdigest() == g["ends_sha256"]
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7, 8, 9, -1])
+def test_every_level_matches_oracle(engine, oracle, corpus, level):
+    data = corpus["lcet10.txt"] + corpus["sum"] + corpus["ptt5"][:200000]
+    want, want_ends, want_adler = oracle.deflate_segments(data, 65536, level)
+    got, ends, adler = engine.deflate_segments(data, 65536, level)
+    assert got == want and ends == want_ends and adler == want_adler
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("level", [1, 6])
+def test_every_strategy_matches_oracle(engine, oracle, corpus, level, strategy):
+    data = corpus["kennedy.xls"][:400000] + corpus_data.png_like(300000) + corpus["alice29.txt"]
+    want, want_ends, _ = oracle.deflate_segments(data, 65536, level, strategy)
+    got, ends, _ = engine.deflate_segments(data, 65536, level, strategy)
+    assert got == want and ends == want_ends
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 11, 261, 262, 263, 32767, 32768, 32769, 65535, 65536, 65537, 65536 + 32768,
+                               131072, 131073, 3 * 65536 + 258])
+def test_ragged_and_tiny_inputs(engine, oracle, corpus, n):
+    """Empty input, sub-window inputs, inputs ending right at / next to refill and segment boundaries."""
+    data = (corpus["asyoulik.txt"] + corpus["cp.html"])[:n]
+    for level in (1, 6):
+        want, want_ends, _ = oracle.deflate_segments(data, 65536, level)
+        got, ends, _ = engine.deflate_segments(data, 65536, level)
+        assert got == want and ends == want_ends, (n, level)
+
+
+@pytest.mark.parametrize("kind", ["zeros", "random", "runs", "sparse"])
+def test_degenerate_data(engine, oracle, kind):
+    rng = np.random.RandomState(5)
+    n = 5 * 65536 + 1000
+    if kind == "zeros":
+        data = bytes(n)                       # 258-byte matches everywhere, Q3 two-cycle in prev[]
+    elif kind == "random":
+        data = rng.bytes(n)                   # stored blocks
+    elif kind == "runs":
+        data = bytes(np.repeat(rng.randint(0, 256, size=n // 40 + 1).astype(np.uint8), 40)[:n])
+    else:
+        data = corpus_data.sparse_image(512, 700)[:n]
+    for level, strategy in ((1, 0), (6, 0), (9, 0), (6, 3), (6, 2), (6, 1)):
+        want, want_ends, _ = oracle.deflate_segments(data, 65536, level, strategy)
+        got, ends, _ = engine.deflate_segments(data, 65536, level, strategy)
+        assert got == want and ends == want_ends, (kind, level, strategy)
+
+
+def test_symbol_count_hits_block_limit_exactly(engine, oracle):
+    """HuffmanOnly: every full block is exactly 16383 literals (Q9); 4 * 16383 + 4 = 65536 exercises the boundary."""
+    rng = np.random.RandomState(9)
+    data = bytes(rng.randint(32, 127, size=4 * 65536, dtype=np.uint8))
+    for ss in (65536, 131072):
+        want, want_ends, _ = oracle.deflate_segments(data, ss, 6, 2)
+        got, ends, _ = engine.deflate_segments(data, ss, 6, 2)
+        assert got == want and ends == want_ends
+
+
+def test_256k_segments_levels_6_and_9(engine, oracle):
+    data = corpus_data.mixed_entropy(6 * 262144 + 5000)     # BASELINE config 3 shape
+    for level in (6, 9):
+        want, want_ends, _ = oracle.deflate_segments(data, 262144, level)
+        got, ends, _ = engine.deflate_segments(data, 262144, level)
+        assert got == want and ends == want_ends
+
+
+def test_multiplicative_hash_variant(engine, oracle, corpus):
+    data = corpus["plrabn12.txt"][:300000]
+    for level in (1, 6):
+        want, _, _ = oracle.deflate_segments(data, 65536, level, 0, 1)
+        got, _, _ = engine.deflate_segments(data, 65536, level, 0, 1)
+        assert got == want
+
+
+def test_sharded_ranges_concatenate_to_the_single_stream(engine, oracle, corpus):
+    """What the multi-GPU path relies on: compressing contiguous segment ranges separately (first_segment_index, no
+    header / trailer on later shards) and concatenating gives the single-stream bytes."""
+    data = _blob(corpus)
+    ss = 65536
+    want, want_ends, want_adler = oracle.deflate_segments(data, ss, 6)
+    nseg = (len(data) + ss - 1) // ss
+    cuts = [0, 7, 8, 30, nseg]
+    parts, adler = [], 1
+    from zlibstream_b200 import adler32_combine
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        chunk = data[a * ss:b * ss]
+        halo = data[a * ss - 32768:a * ss] if a else None
+        got, ends, ad = engine.deflate_segments(chunk, ss, 6, 0, first_segment_index=a, halo=halo, header=(a == 0), trailer=False)
+        parts.append(got)
+        adler = adler32_combine(adler, ad, len(chunk))
+    stream = b"".join(parts) + b"\x03\x00" + adler.to_bytes(4, "big")
+    assert stream == want and adler == want_adler
+
+
+def test_rle_needs_the_halo_byte(engine, oracle, corpus):
+    """Q14: an Rle segment may start with a distance-1 copy of the previous segment's last byte."""
+    data = corpus["ptt5"]
+    ss = 65536
+    want, _, _ = oracle.deflate_segments(data, ss, 6, 3)
+    a = 3
+    head, _, ad0 = engine.deflate_segments(data[:a * ss], ss, 6, 3, trailer=False)
+    tail, _, ad1 = engine.deflate_segments(data[a * ss:], ss, 6, 3, first_segment_index=a, halo=data[a * ss - 32768:a * ss],
+                                           header=False, trailer=False)
+    assert (head + tail) == want[:-6]
+
+
+def test_output_buffer_too_small_is_buf_error(engine, corpus):
+    import ctypes
+    from zlibstream_b200 import _native
+    lib = _native.load()
+    data = corpus["alice29.txt"]
+    out = ctypes.create_string_buffer(1000)
+    n = ctypes.c_size_t(0)
+    ad = ctypes.c_uint32(0)
+    rc = lib.zsb_deflate_segments(engine._h, data, len(data), 65536, 6, 0, 0, 0, None, 0, out, 1000, ctypes.byref(n), None,
+                                  ctypes.byref(ad))
+    assert rc == -5 and engine.message == "buffer error" and n.value > 1000    # CompressionState.ZBUFERROR
+
+
+def test_argument_errors(engine):
+    from zlibstream_b200 import ZlibStreamException
+    for kw in (dict(level=10), dict(level=-2), dict(strategy=5), dict(seg_size=65536 + 512), dict(seg_size=32768)):
+        args = dict(seg_size=65536, level=6, strategy=0)
+        args.update(kw)
+        with pytest.raises(ZlibStreamException, match="deflating: "):
+            engine.deflate_segments(b"x" * 100, args["seg_size"], args["level"], args["strategy"])
+
+
+def test_large_property_round_trip(engine):
+    """BASELINE-size shape at reduced length (256 MiB): size-independent properties -- stock zlib decodes the stream to
+    the input, every segment ends with the marker, Adler-32 matches, the device inflater round-trips it."""
+    import torch
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import synth
+    n = 256 << 20
+    ss = 65536
+    data = synth.text_like(n, seed=11, device="cuda")
+    cap = engine.deflate_bound(n, ss)
+    out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    ends = torch.empty(n // ss, dtype=torch.int64, device="cuda")
+    out_len, adler = engine.deflate_segments_device(data.data_ptr(), n, ss, 1, 0, 0, 0, out.data_ptr(), cap, ends.data_ptr())
+    host = data.cpu().numpy().tobytes()
+    comp = out[:out_len].cpu().numpy().tobytes()
+    assert adler == zlib.adler32(host)
+    e = ends.cpu().numpy()
+    assert all(comp[int(x) - 4:int(x)] == b"\x00\x00\xff\xff" for x in e[::97])
+    assert zlib.decompress(comp) == host
+    dec = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dl, dad = engine.inflate_segments_device(out.data_ptr(), out_len, ends.data_ptr(), n // ss, ss, dec.data_ptr(), n)
+    assert dl == n and dad == adler and torch.equal(dec, data)

@@ -1,0 +1,113 @@
+"""GPU inflate of full-flush-segmented streams, Adler-32, and the stream classes, all through the C ABI."""
+import io
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus_data
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [1, 8, 215, 1024, 1024 + 15, 2034, 4096, 5552, 5553, 65535, 65536, 65537, (1 << 22) + 13])
+def test_adler32_matches_zlib(engine, n):
+    d = np.random.RandomState(1).bytes(n)                  # Adler32Tests.cs:22-40 lengths and beyond
+    for seed in (1, 0, 0x00AB00CD):
+        assert engine.adler32(d, seed) == zlib.adler32(d, seed)
+
+
+def test_adler32_empty_returns_seed(engine):
+    from zlibstream_b200 import Adler32
+    for seed in (0, 1, 2):
+        assert Adler32.Calculate(b"", seed, engine) == seed  # Adler32Tests.cs:13-20
+
+
+def test_adler32_worst_case_bytes(engine):
+    d = b"\xff" * (3 * 65536 + 5551)
+    assert engine.adler32(d) == zlib.adler32(d)
+
+
+@pytest.mark.parametrize("level,strategy,ss", [(1, 0, 65536), (6, 0, 65536), (9, 0, 262144), (6, 1, 65536), (6, 2, 65536),
+                                               (1, 4, 65536), (3, 0, 131072)])
+def test_inflate_reference_streams(engine, oracle, corpus, level, strategy, ss):
+    """Streams produced by the oracle (= the reference's bytes): decoded bytes and Adler-32 must be exact."""
+    data = b"".join(corpus[k] for k in sorted(corpus))
+    comp, ends, adler = oracle.deflate_segments(data, ss, level, strategy)
+    out, ad = engine.inflate_segments(comp, ends, ss, len(data))
+    assert out == data and ad == adler == zlib.adler32(data)
+
+
+def test_inflate_stored_and_degenerate(engine, oracle):
+    rng = np.random.RandomState(3)
+    for data in (rng.bytes(300001), bytes(400000), b"a", corpus_data.sparse_image(256, 300)):
+        comp, ends, adler = oracle.deflate_segments(data, 65536, 6)
+        out, ad = engine.inflate_segments(comp, ends, 65536, len(data))
+        assert out == data and ad == adler
+
+
+def test_inflate_detects_corruption(engine, oracle, corpus):
+    from zlibstream_b200 import ZlibStreamException
+    data = corpus["alice29.txt"]
+    comp, ends, adler = oracle.deflate_segments(data, 65536, 6)
+    bad = bytearray(comp)
+    bad[-1] ^= 1
+    with pytest.raises(ZlibStreamException, match="inflating: incorrect data check"):     # Inflate.cs:339
+        engine.inflate_segments(bytes(bad), ends, 65536, len(data))
+    bad = bytearray(comp)
+    bad[0] = 0x79
+    with pytest.raises(ZlibStreamException, match="inflating: unknown compression method"):  # Inflate.cs:134
+        engine.inflate_segments(bytes(bad), ends, 65536, len(data))
+    bad = bytearray(comp)
+    bad[1] ^= 0x01
+    with pytest.raises(ZlibStreamException, match="inflating: incorrect header check"):     # Inflate.cs:166
+        engine.inflate_segments(bytes(bad), ends, 65536, len(data))
+    bad = bytearray(comp)
+    for i in range(3000, 3040):
+        bad[i] ^= 0x5A
+    with pytest.raises(ZlibStreamException, match="inflating: "):
+        engine.inflate_segments(bytes(bad), ends, 65536, len(data))
+
+
+def test_stream_classes_round_trip(engine, oracle, corpus):
+    """ZlibOutputStream / ZlibInputStream with FullFlush: one Write per segment (ZlibOutputStream.cs:146), Dispose
+    finishes; TotalOut and the bytes are the reference's."""
+    from zlibstream_b200 import CompressionLevel, FlushMode, ZlibInputStream, ZlibOptions, ZlibOutputStream
+    data = b"".join(corpus[k] for k in sorted(corpus))
+    ss = 65536
+    want, want_ends, _ = oracle.deflate_segments(data, ss, 6)
+    sink = io.BytesIO()
+    opts = ZlibOptions(CompressionLevel=CompressionLevel.Level6, FlushMode=FlushMode.FullFlush)
+    z = ZlibOutputStream(sink, opts, engine=engine, batch_segments=16)
+    for off in range(0, len(data), ss):
+        z.Write(data, off, min(ss, len(data) - off))
+    z.Flush()
+    assert z.TotalIn == len(data) and z.TotalOut == want_ends[-1] and z.SegmentEndOffsets == want_ends
+    z.close()
+    assert sink.getvalue() == want and z.TotalOut == len(want)
+    zi = ZlibInputStream(io.BytesIO(want), segment_size=ss, segment_end_offsets=want_ends, uncompressed_size=len(data),
+                         engine=engine)
+    got = bytearray(len(data))
+    pos = 0
+    while pos < len(data):
+        r = zi.Read(got, pos, 8192)                         # ZlibStreamTests.Roundtrip.cs:100-103 read pattern
+        if r == 0:
+            break
+        pos += r
+    assert bytes(got) == data and zi.Adler == zlib.adler32(data)
+
+
+def test_stream_class_argument_behaviour(engine):
+    from zlibstream_b200 import CompressionLevel, FlushMode, ZlibOptions, ZlibOutputStream, ZlibStreamException
+    with pytest.raises(ValueError):
+        ZlibOutputStream(None, CompressionLevel.Level6, engine=engine)
+    z = ZlibOutputStream(io.BytesIO(), ZlibOptions(CompressionLevel=CompressionLevel.Level6), engine=engine)
+    with pytest.raises(ZlibStreamException, match="deflating: "):   # NoFlush is not on the device path
+        z.write(b"x" * 65536)
+    with pytest.raises(io.UnsupportedOperation):
+        z.seek(0)
+    sink = io.BytesIO()
+    z = ZlibOutputStream(sink, ZlibOptions(CompressionLevel=CompressionLevel.Level6, FlushMode=FlushMode.FullFlush), engine=engine)
+    z.write(b"")
+    z.close()
+    assert sink.getvalue().hex() == "789c030000000001"      # empty stream: header, final empty static block, Adler(1)

@@ -75,6 +75,7 @@ struct zsb_ctx {
     // scratch
     DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status;
     uint16_t* crc_tab = nullptr;
+    unsigned long long* lz_stats = nullptr;  // 32 counters, only with ZSB_LZ_STATS=1
     // timing of the last call
     std::vector<cudaEvent_t> ev;  // pairs
     std::vector<int> ev_kind;     // 0 lz77, 1 huffman, 2 inflate
@@ -204,6 +205,10 @@ int zsb_ctx_create(int device, zsb_ctx** out)
         zsb_ctx_destroy(ctx);
         return ZSB_MEM_ERROR;
     }
+    if (env_size("ZSB_LZ_STATS", 0)) {
+        if (cudaMalloc(&ctx->lz_stats, 32 * sizeof(unsigned long long)) != cudaSuccess) { zsb_ctx_destroy(ctx); return ZSB_MEM_ERROR; }
+        cudaMemset(ctx->lz_stats, 0, 32 * sizeof(unsigned long long));
+    }
     *out = ctx;
     return ZSB_OK;
 }
@@ -218,6 +223,7 @@ void zsb_ctx_destroy(zsb_ctx* ctx)
                       &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status};
     for (DevBuf* b : bufs) b->release();
     if (ctx->crc_tab) cudaFree(ctx->crc_tab);
+    if (ctx->lz_stats) cudaFree(ctx->lz_stats);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -362,6 +368,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         L.seg_adler = ctx->seg_adler.as<uint2>() + s0;
         L.work_counter = d_work;
         L.crc_tab = ctx->crc_tab;
+        L.stats = ctx->lz_stats;
         CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
         timing_mark(ctx, 0, true);
         CU(launch_lz77(L, ctx->num_sms, st));
@@ -595,6 +602,12 @@ extern "C" ZSB_API int zsb_debug_fetch(zsb_ctx* ctx, int what, uint64_t byte_off
         case 3: b = &ctx->layout; break;     // SegLayout [seg]
         case 4: b = &ctx->codes; break;      // BlockCodesDev [seg][max_blocks]
         case 5: b = &ctx->seg_adler; break;  // uint2 [seg]
+        case 6: {                            // LZ77 diagnostics counters (ZSB_LZ_STATS=1), cumulative
+            if (!ctx->lz_stats || byte_offset + bytes > 32 * sizeof(unsigned long long)) return fail(ctx, ZSB_BUF_ERROR, "no stats");
+            CU(cudaSetDevice(ctx->device));
+            CU(cudaMemcpy(dst, reinterpret_cast<const uint8_t*>(ctx->lz_stats) + byte_offset, bytes, cudaMemcpyDeviceToHost));
+            return ZSB_OK;
+        }
         default: return ZSB_STREAM_ERROR;
     }
     if (byte_offset + bytes > b->cap) return fail(ctx, ZSB_BUF_ERROR, "debug fetch out of range");

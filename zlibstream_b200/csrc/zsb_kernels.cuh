@@ -23,6 +23,7 @@ struct Lz77Params {
     uint2* seg_adler;         // [nseg] (s1, s2) of each segment, seed 1
     unsigned int* work_counter;
     const uint16_t* crc_tab;  // 4 * 256
+    unsigned long long* stats; // optional diagnostics counters (ZSB_LZ_STATS=1), else nullptr
 };
 size_t lz77_smem_bytes();
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream);

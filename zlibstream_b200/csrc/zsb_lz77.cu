@@ -17,7 +17,9 @@ namespace zsb {
 namespace {
 
 constexpr int LZ_THREADS = 256;
-constexpr int WIN_PAD = 16;
+constexpr int WIN_PAD = 64;
+constexpr int SLOT_COUNT = 4096;
+constexpr uint32_t SLOT_MASK = SLOT_COUNT - 1;
 
 struct ParserState {
     int str_start, lookahead, block_start, match_length, prev_length, match_start, prev_match, match_available;
@@ -35,6 +37,8 @@ struct Smem {
     uint16_t* head;  // HASH_SIZE
     uint16_t* prev;  // W_SIZE
     uint16_t* crc;   // 4 * 256, low 16 bits of the slice-by-4 CRC-32C tables
+    uint32_t* slot;  // SLOT_COUNT: first-lane-per-hash-slot arbitration of the batch parser
+    uint32_t* batch_seq;
 };
 
 __device__ __forceinline__ uint32_t hash_of(const Smem& sm, uint32_t v, int hash_variant)
@@ -148,44 +152,327 @@ __device__ __forceinline__ bool fill_needed(const ParserState& s)
     return s.avail_in > 0 || s.str_start >= WINDOW_SIZE - MIN_LOOKAHEAD;
 }
 
-// Deflate.Fast.cs:20-128.  Runs until the window needs refilling / sliding or the segment is done.
-__device__ void parse_fast(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
-                           int hash_variant)
+// One iteration of the DeflateFast loop body (Deflate.Fast.cs:43-112) at a position that does not need Fill_window.
+__device__ void fast_step(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
+                          int hash_variant)
 {
+    int hash_head = 0;
+    if (s.lookahead >= MIN_MATCH) hash_head = insert_string(sm, s.str_start, hash_variant);
+    if (hash_head != 0 && (s.str_start - hash_head) <= MAX_DIST) {
+        if (strategy != 2 /* HuffmanOnly */) s.match_length = longest_match(sm, s, cfg, hash_head);
+    }
+    bool bflush;
+    if (s.match_length >= MIN_MATCH) {
+        bflush = tally_dist(s, o, s.str_start - s.match_start, s.match_length - MIN_MATCH);
+        s.lookahead -= s.match_length;
+        if (s.match_length <= cfg.lazy && s.lookahead >= MIN_MATCH) {
+            s.match_length--;
+            do {
+                s.str_start++;
+                insert_string(sm, s.str_start, hash_variant);
+            } while (--s.match_length != 0);
+            s.str_start++;
+        } else {
+            s.str_start += s.match_length;
+            s.match_length = 0;
+        }
+    } else {
+        bflush = tally_lit(s, o, sm.win[s.str_start]);
+        s.lookahead--;
+        s.str_start++;
+    }
+    if (bflush) close_block(s, o);
+}
+
+__device__ __forceinline__ void bcast_state(ParserState& s)
+{
+    int* f = reinterpret_cast<int*>(&s);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(ParserState) / sizeof(int)); k++) f[k] = __shfl_sync(0xffffffffu, f[k], 0);
+}
+
+// Common prefix length of the window strings at p and c, capped at MAX_MATCH (what Longest_match's pre-filters plus
+// Compare256 amount to: a candidate replaces the best match iff this value exceeds best_len).
+__device__ __forceinline__ int common_prefix258(const uint8_t* win, int p, int c)
+{
+    int len = 0;
+    while (len < MAX_MATCH + 2) {
+        const uint32_t x = lds_u32_unaligned(win, p + len) ^ lds_u32_unaligned(win, c + len);
+        if (x) {
+            len += (__ffs(x) - 1) >> 3;
+            break;
+        }
+        len += 4;
+    }
+    return len < MAX_MATCH ? len : MAX_MATCH;
+}
+
+// 16 window bytes at any byte index (the array is padded), as four little-endian words.
+__device__ __forceinline__ void lds16_unaligned(const uint8_t* base, int idx, uint32_t (&w)[4])
+{
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (idx & ~3));
+    const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+    const int sh = (idx & 3) * 8;
+    w[0] = __funnelshift_r(a0, a1, sh);
+    w[1] = __funnelshift_r(a1, a2, sh);
+    w[2] = __funnelshift_r(a2, a3, sh);
+    w[3] = __funnelshift_r(a3, a4, sh);
+}
+
+// Common prefix of two 16-byte strings: 0..16.
+__device__ __forceinline__ int prefix16(const uint32_t (&a)[4], const uint32_t (&b)[4])
+{
+    const uint32_t x0 = a[0] ^ b[0], x1 = a[1] ^ b[1], x2 = a[2] ^ b[2], x3 = a[3] ^ b[3];
+    int L = 16;
+    if (x3) L = 12 + ((__ffs(x3) - 1) >> 3);
+    if (x2) L = 8 + ((__ffs(x2) - 1) >> 3);
+    if (x1) L = 4 + ((__ffs(x1) - 1) >> 3);
+    if (x0) L = (__ffs(x0) - 1) >> 3;
+    return L;
+}
+
+// Whole warp: common prefix of the strings at p and c beyond their first `from` bytes (known equal), capped at MAX_MATCH.
+__device__ __forceinline__ int warp_extend_match(const uint8_t* win, int p, int c, int from, int lane)
+{
+    int len = from;
+    while (len < MAX_MATCH) {
+        const int off = len + 4 * lane;
+        const uint32_t x = lds_u32_unaligned(win, p + off) ^ lds_u32_unaligned(win, c + off);
+        const uint32_t ne = __ballot_sync(0xffffffffu, x != 0);
+        if (ne) {
+            const int first = __ffs(ne) - 1;
+            const uint32_t xf = __shfl_sync(0xffffffffu, x, first);
+            len += 4 * first + ((__ffs(xf) - 1) >> 3);
+            break;
+        }
+        len += 128;
+    }
+    return len < MAX_MATCH ? len : MAX_MATCH;
+}
+
+// DeflateFast (Deflate.Fast.cs:20-128) by one warp: 32 consecutive positions are evaluated speculatively as parse
+// points (lane i = str_start + i) against the hash table as it stands before the batch; a ballot walk then resolves
+// the greedy parse, and the inserts of the positions the reference would have inserted are committed in position
+// order.  A position whose hash also occurs earlier in the same batch cannot be speculated on (its chain would start
+// inside the batch): when the parse reaches one, the batch ends there and the next one starts at it.  A position the
+// Q3 pre-insert touched (head[h] >= position) runs the reference iteration literally on lane 0.
+// "Occurs earlier in the batch" is decided through a small slot table (atomicMax of a batch-sequence | lane key per
+// hash slot; __match_any_sync costs ~12 cycles per distinct value on sm_100, 385 cycles for 32 hashes): a lane is
+// clean iff it is the first lane of the batch in its slot, which errs only towards "not clean".
+// Runs until the window needs refilling / sliding or the segment is done.
+__device__ void parse_fast_warp(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
+                                int hash_variant, unsigned long long* stats)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t below = (1u << lane) - 1u;
+    const bool quick = cfg.chain <= 4 && cfg.nice <= 16;  // level 1: the whole chain is probed in one round of loads
+    long long st_t0 = 0, st_t1 = 0, st_t2 = 0, st_t3 = 0;
+    uint32_t seq = *sm.batch_seq;
     for (;;) {
         if (s.lookahead < MIN_LOOKAHEAD) {
-            if (fill_needed(s)) return;
-            if (s.lookahead == 0) break;
+            if (fill_needed(s)) break;
+            if (s.lookahead == 0) { s.done = 1; break; }
         }
-        int hash_head = 0;
-        if (s.lookahead >= MIN_MATCH) hash_head = insert_string(sm, s.str_start, hash_variant);
-        if (hash_head != 0 && (s.str_start - hash_head) <= MAX_DIST) {
-            if (strategy != 2 /* HuffmanOnly */) s.match_length = longest_match(sm, s, cfg, hash_head);
+        // positions str_start .. str_start + nact - 1 reach the top of the loop without triggering Fill_window
+        int nact;
+        if (s.avail_in > 0) nact = s.lookahead - (MIN_LOOKAHEAD - 1);
+        else {
+            const int top = s.str_start + s.lookahead;
+            int first_trigger = top - (MIN_LOOKAHEAD - 1);
+            if (first_trigger < WINDOW_SIZE - MIN_LOOKAHEAD) first_trigger = WINDOW_SIZE - MIN_LOOKAHEAD;
+            nact = first_trigger - s.str_start;
+            if (nact > s.lookahead) nact = s.lookahead;
         }
-        bool bflush;
-        if (s.match_length >= MIN_MATCH) {
-            bflush = tally_dist(s, o, s.str_start - s.match_start, s.match_length - MIN_MATCH);
-            s.lookahead -= s.match_length;
-            if (s.match_length <= cfg.lazy && s.lookahead >= MIN_MATCH) {
-                s.match_length--;
-                do {
-                    s.str_start++;
-                    insert_string(sm, s.str_start, hash_variant);
-                } while (--s.match_length != 0);
-                s.str_start++;
+        if (nact > 32) nact = 32;
+        if (nact > BLOCK_SYMS - s.last_lit) nact = BLOCK_SYMS - s.last_lit;
+        const uint32_t act = nact >= 32 ? 0xffffffffu : (1u << nact) - 1u;
+
+        const int S = s.str_start, LA = s.lookahead;
+        const int p = S + lane, la = LA - lane;
+        if (stats) st_t0 = clock64();
+        // ---- speculative phase ----
+        const bool hashed = la >= MIN_MATCH;
+        uint32_t h = 0;
+        int c0 = 0;
+        uint32_t scan[4];
+        lds16_unaligned(sm.win, p, scan);
+        bool first_in_slot = true;
+        seq++;
+        if (hashed) {
+            h = hash_of(sm, __funnelshift_r(scan[0], scan[1], 16), hash_variant);
+            atomicMax(&sm.slot[h & SLOT_MASK], (seq << 5) | (uint32_t)(31 - lane));
+            c0 = sm.head[h];
+        }
+        __syncwarp();
+        if (hashed) first_in_slot = sm.slot[h & SLOT_MASK] == ((seq << 5) | (uint32_t)(31 - lane));
+        const bool hard = hashed && c0 >= p;                 // Q2/Q3: the refill pre-inserted this position (or the next)
+        const bool dirty = hashed && (!first_in_slot || hard);
+        int best = MIN_MATCH - 1, mstart = 0;
+        bool ext = false;  // best == 16 stands for "at least 16": the exact length is found if the position is a parse point
+        if (hashed && !dirty && lane < nact && c0 != 0 && p - c0 <= MAX_DIST && strategy != 2) {
+            const int nice = cfg.nice < la ? cfg.nice : la;
+            const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
+            if (quick) {
+                // Longest_match (Deflate.cs:1022-1100) with the <= 4 chain links fetched up front and their windows
+                // compared side by side; the selection below visits them in the reference's order.
+                const int c1 = sm.prev[c0 & W_MASK];
+                const int c2 = sm.prev[c1 & W_MASK];
+                const int c3 = sm.prev[c2 & W_MASK];
+                uint32_t w0[4], w1[4], w2[4], w3[4];
+                lds16_unaligned(sm.win, c0, w0);
+                lds16_unaligned(sm.win, c1, w1);
+                lds16_unaligned(sm.win, c2, w2);
+                lds16_unaligned(sm.win, c3, w3);
+                const int L0 = prefix16(scan, w0), L1 = prefix16(scan, w1), L2 = prefix16(scan, w2), L3 = prefix16(scan, w3);
+                bool go = c0 < p;
+                if (go && L0 > best) { best = L0; mstart = c0; if (L0 >= nice) go = false; }
+                go = go && c1 > limit && cfg.chain > 1 && c1 < p;
+                if (go && L1 > best) { best = L1; mstart = c1; if (L1 >= nice) go = false; }
+                go = go && c2 > limit && cfg.chain > 2 && c2 < p;
+                if (go && L2 > best) { best = L2; mstart = c2; if (L2 >= nice) go = false; }
+                go = go && c3 > limit && cfg.chain > 3 && c3 < p;
+                if (go && L3 > best) { best = L3; mstart = c3; }
+                ext = best == 16;
             } else {
-                s.str_start += s.match_length;
-                s.match_length = 0;
+                int chain = cfg.chain;
+                int cur = c0;
+                do {
+                    if (cur >= p) break;  // Deflate.cs:1067-1070 (reachable through the Q3 two-cycle)
+                    uint32_t cw[4];
+                    lds16_unaligned(sm.win, cur, cw);
+                    const int nxt = sm.prev[cur & W_MASK];
+                    int L = prefix16(scan, cw);
+                    if (L == 16 && nice > 16) {  // nice_match exceeds the probe (level 3): finish the compare here
+                        L = common_prefix258(sm.win, p, cur);
+                        if (L > best) { best = L; mstart = cur; if (L >= nice) break; }
+                    } else if (L > best) {
+                        best = L;
+                        mstart = cur;
+                        if (L == 16) { ext = true; break; }
+                        if (L >= nice) break;
+                    }
+                    cur = nxt;
+                } while (cur > limit && --chain != 0);
             }
-        } else {
-            bflush = tally_lit(s, o, sm.win[s.str_start]);
-            s.lookahead--;
-            s.str_start++;
         }
-        if (bflush) close_block(s, o);
+        int len = best < la ? best : la;
+        const bool is_match = len >= MIN_MATCH;
+        int endl = lane + (is_match ? len : 1);   // lane index of the next parse point if this lane is one
+        const uint32_t Mm = __ballot_sync(0xffffffffu, is_match) & act;
+        const uint32_t Dm = __ballot_sync(0xffffffffu, dirty) & act;
+        const uint32_t Xm = __ballot_sync(0xffffffffu, ext);
+        const uint32_t Hd = __ballot_sync(0xffffffffu, hard);
+        const uint32_t H3 = __ballot_sync(0xffffffffu, hashed);
+        if (stats) st_t1 = clock64();
+        // ---- resolve the greedy parse: hop from match to match, literals in between are parse points ----
+        int cur = 0;
+        uint32_t vis = 0;          // lanes whose match is taken
+        bool hit_dirty = false;
+        const uint32_t stops = Mm | Dm;
+        for (;;) {
+            const uint32_t stop = stops & (0xffffffffu << cur);
+            if (stop == 0) { cur = nact; break; }
+            const int nxt = __ffs(stop) - 1;
+            if ((Dm >> nxt) & 1u) { cur = nxt; hit_dirty = true; break; }
+            if ((Xm >> nxt) & 1u) {  // long match at a parse point: the warp finishes the compare
+                const int ms = __shfl_sync(0xffffffffu, mstart, nxt);
+                const int full = warp_extend_match(sm.win, S + nxt, ms, 16, lane);
+                if (lane == nxt) {
+                    len = full < la ? full : la;
+                    endl = lane + len;
+                }
+            }
+            vis |= 1u << nxt;
+            cur = __shfl_sync(0xffffffffu, endl, nxt);
+            if (cur >= nact) break;
+        }
+        // lanes covered by a taken match are not parse points; the interior of a short one is still inserted
+        const bool taken = (vis >> lane) & 1u;
+        const bool is_short = taken && len <= cfg.lazy && la - len >= MIN_MATCH;   // Deflate.Fast.cs:81
+        uint32_t cover = 0, shortins = 0;
+        if (taken) {
+            const uint32_t upto = endl >= 32 ? 0xffffffffu : (1u << endl) - 1u;
+            cover = upto & ~((2u << lane) - 1u);
+            if (is_short) shortins = cover;
+        }
+        cover = __reduce_or_sync(0xffffffffu, cover);
+        shortins = __reduce_or_sync(0xffffffffu, shortins);
+        const uint32_t tailm = __ballot_sync(0xffffffffu, is_short && endl > 32);
+        const uint32_t done_mask = cur >= 32 ? 0xffffffffu : (1u << cur) - 1u;
+        const uint32_t pm = done_mask & ~cover;              // parse points
+        const uint32_t im = (pm & H3) | shortins;            // inserted positions
+        if (stats) st_t2 = clock64();
+        // ---- symbols (Tr_tally_*): parse points in position order ----
+        const int nsym = __popc(pm);
+        if ((pm >> lane) & 1u) {
+            const uint32_t v = taken ? ((uint32_t)(p - mstart) | ((uint32_t)(len - MIN_MATCH) << 16)) : ((scan[0] & 0xFFu) << 16);
+            o.sym[s.sym_total + __popc(pm & below)] = v;
+        }
+        // ---- commit InsertString of every inserted position, in position order ----
+        // Clean lanes are the only ones of their hash so far in the batch: they go first, side by side.  The others
+        // (a later lane of a hash already seen) follow one at a time, as the reference would execute them.
+        const uint32_t serial_ins = im & ~__ballot_sync(0xffffffffu, first_in_slot && !hard);
+        if (((im & ~serial_ins) >> lane) & 1u) {
+            sm.prev[p & W_MASK] = (uint16_t)c0;
+            sm.head[h] = (uint16_t)p;
+        }
+        __syncwarp();
+        for (uint32_t m = serial_ins; m != 0; m &= m - 1) {
+            if (lane == __ffs(m) - 1) {
+                const int curh = sm.head[h];
+                if (curh != p) {   // Q2
+                    sm.prev[p & W_MASK] = (uint16_t)curh;
+                    sm.head[h] = (uint16_t)p;
+                }
+            }
+            __syncwarp();
+        }
+        s.sym_total += nsym;
+        s.last_lit += nsym;
+        s.str_start = S + cur;
+        s.lookahead = LA - cur;
+        s.match_length = 0;
+        if (tailm != 0) {   // the interior of a short match runs past lane 31
+            const int last = S + __shfl_sync(0xffffffffu, endl, __ffs(tailm) - 1) - 1;
+            if (lane == 0)
+                for (int q = S + 32; q <= last; q++) insert_string(sm, q, hash_variant);
+            __syncwarp();
+        }
+        if (s.last_lit == BLOCK_SYMS) {
+            ParserState t = s;
+            if (lane == 0) close_block(t, o);
+            else { t.nblocks++; t.last_lit = 0; t.block_start = t.str_start; }
+            s = t;
+        }
+        if (stats) st_t3 = clock64();
+        const bool serial = hit_dirty && ((Hd >> cur) & 1u);
+        if (serial) {
+            if (lane == 0) fast_step(sm, s, o, cfg, strategy, hash_variant);
+            bcast_state(s);
+            __syncwarp();
+        }
+        if (stats && lane == 0) {
+            const long long t4 = clock64();
+            atomicAdd(stats + 0, 1ull);
+            atomicAdd(stats + 1, (unsigned long long)cur);
+            atomicAdd(stats + 2, hit_dirty ? 1ull : 0ull);
+            atomicAdd(stats + 3, (unsigned long long)nact);
+            atomicAdd(stats + 4, (unsigned long long)(st_t1 - st_t0));
+            atomicAdd(stats + 5, (unsigned long long)(st_t2 - st_t1));
+            atomicAdd(stats + 6, (unsigned long long)(st_t3 - st_t2));
+            atomicAdd(stats + 7, (unsigned long long)(t4 - st_t3));
+            atomicAdd(stats + 8, (unsigned long long)__popc(vis));
+            atomicAdd(stats + 9, (unsigned long long)__popc(Dm));
+            atomicAdd(stats + 12, (unsigned long long)__popc(Xm & vis));
+            atomicAdd(stats + 13, serial ? 1ull : 0ull);
+            atomicAdd(stats + 14, (unsigned long long)__popc(serial_ins));
+        }
     }
-    close_block(s, o);  // the end-of-input Flush_block_only(false) (Deflate.Fast.cs:124)
-    s.done = 1;
+    if (lane == 0) *sm.batch_seq = seq;
+    if (s.done) {
+        if (lane == 0) close_block(s, o);  // the end-of-input Flush_block_only(false) (Deflate.Fast.cs:124)
+        else { s.nblocks++; s.last_lit = 0; s.block_start = s.str_start; }
+    }
 }
 
 // Deflate.Slow.cs:18-159
@@ -396,9 +683,13 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
     uint32_t* red = reinterpret_cast<uint32_t*>(bar + 1);  // 2 * 8 * u64
     ParserState* shared_state = reinterpret_cast<ParserState*>(red + 64);
     int* seg_slot = reinterpret_cast<int*>(shared_state + 1);
+    sm.batch_seq = reinterpret_cast<uint32_t*>(seg_slot + 1);
+    sm.slot = reinterpret_cast<uint32_t*>(seg_slot + 4);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 1024; i += LZ_THREADS) sm.crc[i] = P.crc_tab[i];
+    for (int i = tid; i < SLOT_COUNT; i += LZ_THREADS) sm.slot[i] = 0;
+    if (tid == 0) *sm.batch_seq = 0;
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     uint32_t phase = 0;
@@ -475,6 +766,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
         o.max_blocks = (int)P.max_blocks;
 
         for (;;) {
+            const long long st_f0 = P.stats ? clock64() : 0;
             // ---- Fill_window (Deflate.cs:967-1019), executed by the whole CTA ----
             {
                 int str_start = shared_state->str_start, lookahead = shared_state->lookahead;
@@ -529,15 +821,27 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                 }
                 __syncthreads();
             }
+            const long long st_f1 = P.stats ? clock64() : 0;
             // ---- parse until the next refill / slide or the end of the segment ----
-            if (tid == 0) {
+            if (cfg.fn == FN_FAST) {
+                if (tid < 32) {
+                    ParserState s = *shared_state;
+                    __syncwarp();
+                    parse_fast_warp(sm, s, o, cfg, P.strategy, P.hash_variant, P.stats);
+                    __syncwarp();
+                    if (tid == 0) *shared_state = s;
+                }
+            } else if (tid == 0) {
                 ParserState s = *shared_state;
-                if (cfg.fn == FN_FAST) parse_fast(sm, s, o, cfg, P.strategy, P.hash_variant);
-                else if (cfg.fn == FN_SLOW) parse_slow(sm, s, o, cfg, P.strategy, P.hash_variant);
+                if (cfg.fn == FN_SLOW) parse_slow(sm, s, o, cfg, P.strategy, P.hash_variant);
                 else parse_rle(sm, s, o);
                 *shared_state = s;
             }
             __syncthreads();
+            if (P.stats && tid == 0) {
+                atomicAdd(P.stats + 10, (unsigned long long)(st_f1 - st_f0));
+                atomicAdd(P.stats + 11, (unsigned long long)(clock64() - st_f1));
+            }
             if (shared_state->done) break;
         }
         if (tid == 0) {
@@ -550,7 +854,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
 
 size_t lz77_smem_bytes()
 {
-    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16;
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16;
 }
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)

@@ -67,6 +67,7 @@ static code_data g_static_ltree[L_CODES + 2];
 static code_data g_static_dtree[D_CODES];
 static uint16_t g_crc_tab[4][256]; /* low 16 bits are all the 15-bit mask can see, but keep 32 for the API */
 static uint32_t g_crc32c[256];
+static int g_hw_crc; /* set once in the table initialiser: SSE4.2 present (x86 only) */
 static int g_tables_ready = 0;
 
 static unsigned bit_reverse(unsigned code, int len) /* Trees.cs:269-281 */
@@ -137,6 +138,9 @@ static void build_static_tables(void)
         g_crc32c[i] = c;
     }
     (void)g_crc_tab;
+#ifdef __x86_64__
+    g_hw_crc = __builtin_cpu_supports("sse4.2") ? 1 : 0;
+#endif
     g_tables_ready = 1;
 }
 
@@ -599,9 +603,19 @@ static inline uint32_t load_le32(const uint8_t* p)
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+#if defined(__x86_64__) || defined(__i386__)
+#include <nmmintrin.h>
+__attribute__((target("sse4.2"))) static inline uint32_t crc32c_hw(uint32_t val) { return _mm_crc32_u32(0, val); }
+#define ZSO_HAVE_HW_CRC 1
+#endif
+
 static inline uint32_t update_hash(const zso_deflater* s, uint32_t val) /* Deflate.Intrinsics.cs:295-307 */
 {
     if (s->hash_variant == ZSO_HASH_CRC32C) {
+#ifdef ZSO_HAVE_HW_CRC
+        /* the reference itself executes this as one SSE4.2 crc32 instruction (Sse42.Crc32); same value as the table walk */
+        if (g_hw_crc) return crc32c_hw(val);
+#endif
         uint32_t crc = 0;
         for (int i = 0; i < 4; i++) {
             crc = g_crc32c[(crc ^ val) & 0xFF] ^ (crc >> 8);
@@ -667,9 +681,24 @@ static void fill_window(zso_deflater* s) /* Deflate.cs:967-1019 */
 
 static inline int compare256(const uint8_t* a, const uint8_t* b) /* Deflate.Intrinsics.cs:19-162 */
 {
+    /* 8 bytes per step (the reference uses 32-byte AVX2 / 16-byte SSE2 steps); same result as the byte loop */
     int len = 0;
-    while (len < 256 && a[len] == b[len]) len++;
-    return len;
+    while (len < 256) {
+        uint64_t x, y;
+        memcpy(&x, a + len, 8);
+        memcpy(&y, b + len, 8);
+        x ^= y;
+        if (x) {
+#if defined(__BYTE_ORDER__) && __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+            return len + (__builtin_ctzll(x) >> 3);
+#else
+            while (a[len] == b[len]) len++;
+            return len;
+#endif
+        }
+        len += 8;
+    }
+    return 256;
 }
 
 static inline unsigned load_le16(const uint8_t* p) { return (unsigned)p[0] | ((unsigned)p[1] << 8); }

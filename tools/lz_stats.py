@@ -29,7 +29,12 @@ def main():
         data = synth.text_like(n, seed=1, device="cuda")
     else:
         import corpus_data
-        blob = getattr(corpus_data, kind)(n)
+        if kind == "blob":
+            c = corpus_data.load_corpus()
+            b = b"".join(c[k] for k in sorted(c))
+            blob = (b * (n // len(b) + 1))[:n]
+        else:
+            blob = getattr(corpus_data, kind)(n)
         data = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
     eng = Engine(0)
     cap = eng.deflate_bound(n, 65536)

@@ -19,6 +19,7 @@ namespace {
 constexpr int LZ_THREADS = 256;
 constexpr int WIN_PAD = 64;
 constexpr int SLOT_COUNT = 4096;
+constexpr int TILE_MAX = 256;   // positions per DeflateSlow tile (= LZ_THREADS, < MIN_LOOKAHEAD)
 constexpr uint32_t SLOT_MASK = SLOT_COUNT - 1;
 
 struct ParserState {
@@ -39,6 +40,8 @@ struct Smem {
     uint16_t* crc;   // 4 * 256, low 16 bits of the slice-by-4 CRC-32C tables
     uint32_t* slot;  // SLOT_COUNT: first-lane-per-hash-slot arbitration of the batch parser
     uint32_t* batch_seq;
+    uint16_t* tile_hh;   // TILE_MAX: what InsertString returned for each position of the current DeflateSlow tile
+    uint2* tile_rec;     // TILE_MAX: Longest_match results of the tile (full / quarter chain budget)
 };
 
 __device__ __forceinline__ uint32_t hash_of(const Smem& sm, uint32_t v, int hash_variant)
@@ -527,6 +530,146 @@ __device__ void parse_slow(const Smem& sm, ParserState& s, const SegOut& o, cons
     s.done = 1;
 }
 
+// ---- DeflateSlow by tiles (levels 4-9) ---------------------------------------------------------------------
+// The lazy parser inserts EVERY position exactly once and in position order (Deflate.Slow.cs:50-53,98-105), so the
+// hash chains do not depend on the parse.  A tile of up to 256 positions (all with lookahead >= MIN_LOOKAHEAD, so no
+// Fill_window can intervene; 256 < MIN_LOOKAHEAD keeps every prev[] slot a search may still read intact) is handled
+// in three steps: (A) one warp inserts the tile's positions in order and keeps what InsertString returned for each,
+// (B) all threads run Longest_match for one position each, (C) one thread replays DeflateSlow with the results.
+// Longest_match depends on the parse only through prev_length: it starts from best_len = prev_length and visits
+// chain >> 2 candidates instead of chain when prev_length >= good_match.  Its result is therefore the longest
+// candidate among the first `budget` ones if that beats prev_length, and (B) keeps that pair for both budgets.
+
+__device__ void slow_tile_insert(const Smem& sm, int S, int T, int hash_variant)   // (A), warp 0
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t seq = *sm.batch_seq;
+    for (int sub = 0; sub < T; sub += 32) {
+        const int i = sub + lane;
+        const bool on = i < T;
+        const int p = S + i;
+        uint32_t h = 0;
+        int c0 = 0;
+        seq++;
+        const uint32_t key = (seq << 5) | (uint32_t)(31 - lane);
+        if (on) {
+            h = hash_of(sm, lds_u32_unaligned(sm.win, p + (MIN_MATCH - 1)), hash_variant);
+            atomicMax(&sm.slot[h & SLOT_MASK], key);
+            c0 = sm.head[h];
+        }
+        __syncwarp();
+        const bool first = on && sm.slot[h & SLOT_MASK] == key;
+        if (first) {   // the only position of its hash so far in this group of 32: InsertString (Deflate.cs:866-877)
+            if (c0 != p) {
+                sm.prev[p & W_MASK] = (uint16_t)c0;
+                sm.head[h] = (uint16_t)p;
+            }
+            sm.tile_hh[i] = (uint16_t)c0;
+        }
+        __syncwarp();
+        for (uint32_t m = __ballot_sync(0xffffffffu, on && !first); m != 0; m &= m - 1) {
+            if (lane == __ffs(m) - 1) {
+                const int cur = sm.head[h];
+                if (cur != p) {
+                    sm.prev[p & W_MASK] = (uint16_t)cur;
+                    sm.head[h] = (uint16_t)p;
+                }
+                sm.tile_hh[i] = (uint16_t)cur;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *sm.batch_seq = seq;
+}
+
+// (B): Longest_match (Deflate.cs:1022-1100) at window position p from hash_head, for both chain budgets.
+// Returns (length | match_start << 9) for the full budget in .x and for chain >> 2 in .y; length 2 = nothing found.
+__device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const LevelCfg& cfg)
+{
+    int best = MIN_MATCH - 1, ms = 0;
+    uint32_t early = 0;
+    bool have_early = false;
+    if (hash_head != 0 && p - hash_head <= MAX_DIST) {
+        const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
+        const int early_budget = cfg.chain >> 2;
+        int chain = cfg.chain, j = 0, cur = hash_head;
+        do {
+            if (cur >= p) break;
+            j++;
+            const int off = best >= 3 ? best - 3 : 0;
+            const uint32_t mask = best >= 3 ? 0xffffffffu : 0x00ffffffu;
+            const int nxt = sm.prev[cur & W_MASK];
+            if (((lds_u32_unaligned(sm.win, cur + off) ^ lds_u32_unaligned(sm.win, p + off)) & mask) == 0) {
+                const int L = common_prefix258(sm.win, p, cur);
+                if (L > best) {
+                    best = L;
+                    ms = cur;
+                    if (L >= cfg.nice) break;
+                }
+            }
+            if (j == early_budget) {
+                early = (uint32_t)best | ((uint32_t)ms << 9);
+                have_early = true;
+            }
+            cur = nxt;
+        } while (cur > limit && --chain != 0);
+    }
+    const uint32_t full = (uint32_t)best | ((uint32_t)ms << 9);
+    return make_uint2(full, have_early ? early : full);
+}
+
+// (C): DeflateSlow (Deflate.Slow.cs:18-159) over the tile [S, S + T), Longest_match / InsertString looked up.
+__device__ void slow_tile_replay(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
+                                 int hash_variant, int S, int T)
+{
+    const int tile_end = S + T;
+    int hash_head = 0;
+    while (s.str_start < tile_end) {
+        const int idx = s.str_start - S;
+        hash_head = sm.tile_hh[idx];
+        s.prev_length = s.match_length;
+        s.prev_match = s.match_start;
+        s.match_length = MIN_MATCH - 1;
+        if (hash_head != 0 && s.prev_length < cfg.lazy && s.str_start - hash_head <= MAX_DIST) {
+            if (strategy != 2) {
+                const uint2 r = sm.tile_rec[idx];
+                const uint32_t e = s.prev_length >= cfg.good ? r.y : r.x;
+                int best = s.prev_length;
+                if ((int)(e & 511u) > best) {
+                    best = (int)(e & 511u);
+                    s.match_start = (int)(e >> 9);
+                }
+                s.match_length = best < s.lookahead ? best : s.lookahead;
+            }
+            if (s.match_length <= 5 &&
+                (strategy == 1 /* Filtered */ || (s.match_length == MIN_MATCH && s.str_start - s.match_start > 4096)))
+                s.match_length = MIN_MATCH - 1;
+        }
+        if (s.prev_length >= MIN_MATCH && s.match_length <= s.prev_length) {
+            const int max_insert = s.str_start + s.lookahead - MIN_MATCH;
+            const bool bflush = tally_dist(s, o, s.str_start - 1 - s.prev_match, s.prev_length - MIN_MATCH);
+            s.lookahead -= s.prev_length - 1;
+            s.prev_length -= 2;
+            do {
+                if (++s.str_start <= max_insert)
+                    hash_head = s.str_start < tile_end ? (int)sm.tile_hh[s.str_start - S] : insert_string(sm, s.str_start, hash_variant);
+            } while (--s.prev_length != 0);
+            s.match_available = 0;
+            s.match_length = MIN_MATCH - 1;
+            s.str_start++;
+            if (bflush) close_block(s, o);
+        } else if (s.match_available != 0) {
+            if (tally_lit(s, o, sm.win[s.str_start - 1])) close_block(s, o);
+            s.str_start++;
+            s.lookahead--;
+        } else {
+            s.match_available = 1;
+            s.str_start++;
+            s.lookahead--;
+        }
+    }
+}
+
 // Deflate.Rle.cs:18-104
 __device__ void parse_rle(const Smem& sm, ParserState& s, const SegOut& o)
 {
@@ -681,10 +824,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
     sm.crc = sm.prev + W_SIZE;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm.crc + 1024);
     uint32_t* red = reinterpret_cast<uint32_t*>(bar + 1);  // 2 * 8 * u64
-    ParserState* shared_state = reinterpret_cast<ParserState*>(red + 64);
+    sm.tile_rec = reinterpret_cast<uint2*>(red + 64);
+    sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + TILE_MAX);
+    sm.tile_hh = reinterpret_cast<uint16_t*>(sm.slot + SLOT_COUNT);
+    ParserState* shared_state = reinterpret_cast<ParserState*>(sm.tile_hh + TILE_MAX);
     int* seg_slot = reinterpret_cast<int*>(shared_state + 1);
     sm.batch_seq = reinterpret_cast<uint32_t*>(seg_slot + 1);
-    sm.slot = reinterpret_cast<uint32_t*>(seg_slot + 4);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 1024; i += LZ_THREADS) sm.crc[i] = P.crc_tab[i];
@@ -831,10 +976,45 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                     __syncwarp();
                     if (tid == 0) *shared_state = s;
                 }
+            } else if (cfg.fn == FN_SLOW) {
+                for (;;) {
+                    const int S = shared_state->str_start;
+                    int T = shared_state->lookahead - (MIN_LOOKAHEAD - 1);
+                    if (T > TILE_MAX) T = TILE_MAX;
+                    __syncthreads();
+                    if (T < 16) {   // too close to a refill / the end of the segment: the reference loop, literally
+                        if (tid == 0) {
+                            ParserState s = *shared_state;
+                            parse_slow(sm, s, o, cfg, P.strategy, P.hash_variant);
+                            *shared_state = s;
+                        }
+                        break;
+                    }
+                    const long long tA = P.stats ? clock64() : 0;
+                    if (tid < 32) slow_tile_insert(sm, S, T, P.hash_variant);
+                    __syncthreads();
+                    const long long tB = P.stats ? clock64() : 0;
+                    if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
+                    __syncthreads();
+                    const long long tC = P.stats ? clock64() : 0;
+                    if (tid == 0) {
+                        ParserState s = *shared_state;
+                        slow_tile_replay(sm, s, o, cfg, P.strategy, P.hash_variant, S, T);
+                        *shared_state = s;
+                    }
+                    __syncthreads();
+                    if (P.stats && tid == 0) {
+                        atomicAdd(P.stats + 0, 1ull);
+                        atomicAdd(P.stats + 1, (unsigned long long)(shared_state->str_start - S));
+                        atomicAdd(P.stats + 3, (unsigned long long)T);
+                        atomicAdd(P.stats + 4, (unsigned long long)(tB - tA));
+                        atomicAdd(P.stats + 5, (unsigned long long)(tC - tB));
+                        atomicAdd(P.stats + 6, (unsigned long long)(clock64() - tC));
+                    }
+                }
             } else if (tid == 0) {
                 ParserState s = *shared_state;
-                if (cfg.fn == FN_SLOW) parse_slow(sm, s, o, cfg, P.strategy, P.hash_variant);
-                else parse_rle(sm, s, o);
+                parse_rle(sm, s, o);
                 *shared_state = s;
             }
             __syncthreads();
@@ -854,7 +1034,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
 
 size_t lz77_smem_bytes()
 {
-    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16;
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 256 * 8 + 256 * 2;
 }
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)

@@ -297,7 +297,7 @@ def run_ours(args):
             "compression_ratio": ratio, "gpu_launches": launches,
             "kernel_ms": {"lz77_segments_kernel": lz, "huffman_stage": sum(hf_ms) / len(hf_ms)},
             "roofline": {"bound": "hbm", "kernel": "lz77_segments_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": _traffic_from_profile(),
+                         "frac": achieved / peak, "traffic": _traffic_from_profile(n),
                          "note": f"algorithmic bytes = input * (1 + ratio) = {algo_bytes:.0f} per launch; peak = {peak_src}; "
                                  "the kernel is dependency-bound, not bandwidth-bound (DESIGN.md)"},
             "clocks": clocks}
@@ -371,10 +371,11 @@ def _hbm_peak():
         return 6650.0, "6.65 TB/s (of fallback, B200_PROFILING.md)"
 
 
-def _traffic_from_profile():
-    """dram bytes per launch of the LZ77 kernel from the committed ncu capture, if any (profiles/lz77_traffic.json)."""
+def _traffic_from_profile(n):
+    """dram bytes per launch of the LZ77 kernel: bytes per input byte from the committed ncu --set full capture
+    (profiles/lz77_traffic.json, taken on a smaller launch of the same workload) times this launch's input bytes."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "lz77_traffic.json")))["dram_bytes_per_launch"]
+        return json.load(open(os.path.join(ROOT, "profiles", "lz77_traffic.json")))["dram_bytes_per_input_byte"] * n
     except Exception:
         return None
 

@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzsb200.so")
+LIB_PATH = os.environ.get("ZSB200_LIB") or os.path.join(_HERE, "libzsb200.so")   # ZSB200_LIB: A/B builds for profiling
 
 ZSB_IN_DEVICE = 0x1
 ZSB_OUT_DEVICE = 0x2

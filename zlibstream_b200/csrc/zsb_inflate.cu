@@ -1,4 +1,4 @@
-// zsb_inflate.cu -- inflate of full-flush-segmented deflate streams: one warp per segment.
+// zsb_inflate.cu -- inflate of full-flush-segmented deflate streams: one group of GW lanes per segment.
 //
 // Replaces Inflate.Decompress (Inflate.cs:103-357, block loop), InflateBlocks.Process
 // (InflateBlocks.cs:130-713), InfCodes.Inflate_fast / Process (InfCodes.cs:106-817) and
@@ -12,8 +12,17 @@ namespace zsb {
 
 namespace {
 
-constexpr int INF_WARPS = 8;
-constexpr int INF_THREADS = INF_WARPS * 32;
+// One GROUP of GW lanes per segment (GW = 8: four segments per warp).  With a whole warp per segment the kernel is
+// issue-bound -- the serial symbol decode keeps one lane of 32 busy, ~50 warp instructions per symbol, 40 warps per SM
+// (32 GB/s measured); narrower groups make every issued instruction serve several segments.
+#ifndef ZSB_INF_GW
+#define ZSB_INF_GW 32
+#endif
+constexpr int GW = ZSB_INF_GW;
+constexpr int INF_THREADS = 64;
+constexpr int INF_GROUPS = INF_THREADS / GW;
+constexpr int PEND_PER_LANE = GW >= 32 ? 1 : 4;   // bytes of an in-flight match copy each lane carries
+constexpr int PEND_MAX = PEND_PER_LANE * GW;
 constexpr int FAST_L = 10;   // root table bits, literal/length
 constexpr int FAST_D = 8;    // root table bits, distance
 
@@ -34,16 +43,34 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-struct BitReader {   // lane 0 only
-    const uint8_t* in;
-    uint64_t pos, end;   // byte offsets inside `in`
+struct BitReader {   // lane 0 only; positions are relative to the segment's first compressed byte
+    const uint8_t* in;   // the segment's first compressed byte
+    uint32_t pos;        // offset of the next byte to load
+    uint32_t end;        // the segment's compressed size
+    uint32_t limit;      // bytes that may be loaded (to the end of the whole compressed buffer, capped)
+    uint32_t fast_end;   // pos < fast_end <=> pos + 16 <= limit: two aligned 64-bit loads stay in bounds
     uint64_t acc;
     int nbits;
+    // Refill to >= 56 bits from two aligned 64-bit loads; bytes past `end` (the next segment's) may enter the
+    // accumulator but are never consumed by a well-formed segment -- consumption is checked against `end` at every
+    // block boundary.
     __device__ __forceinline__ void refill()
     {
-        while (nbits <= 56 && pos < end) {
-            acc |= (uint64_t)in[pos++] << nbits;
-            nbits += 8;
+        if (pos < fast_end) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + pos);
+            const uint64_t* q = reinterpret_cast<const uint64_t*>(addr & ~(uintptr_t)7);
+            const uint64_t a = __ldg(q), b = __ldg(q + 1);
+            const int sh = (int)(addr & 7) * 8;
+            const uint64_t w = sh ? (a >> sh) | (b << (64 - sh)) : a;
+            acc |= w << nbits;
+            const int adv = (63 - nbits) >> 3;
+            pos += (uint32_t)adv;
+            nbits += adv * 8;
+        } else {
+            while (nbits <= 56 && pos < limit) {
+                acc |= (uint64_t)in[pos++] << nbits;
+                nbits += 8;
+            }
         }
     }
     __device__ __forceinline__ bool need(int k)
@@ -51,14 +78,14 @@ struct BitReader {   // lane 0 only
         if (nbits < k) refill();
         return nbits >= k;
     }
-    __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)(acc & ((1ull << k) - 1)); }
+    __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)acc & ((1u << k) - 1u); }   // k <= 16
     __device__ __forceinline__ void drop(int k) { acc >>= k; nbits -= k; }
-    __device__ __forceinline__ uint64_t byte_pos() const { return pos - (uint64_t)(nbits >> 3); }
+    __device__ __forceinline__ uint32_t byte_pos() const { return pos - (uint32_t)(nbits >> 3); }
 };
 
 // Builds one canonical decoding table from sm.lens[base .. base+n).  Whole warp.
 // Returns 0 ok, 1 all zero, -1 oversubscribed, -2 incomplete (InfTree.cs huft_build rules).
-__device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane)
+__device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane, uint32_t gmask)
 {
     uint16_t* fast = dist ? t.fast_d : t.fast_l;
     uint16_t* sorted = dist ? t.sorted_d : t.sorted_l;
@@ -66,7 +93,7 @@ __device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane)
     uint16_t* first = dist ? t.first_d : t.first_l;
     uint16_t* offset = dist ? t.offset_d : t.offset_l;
     const int fast_bits = dist ? FAST_D : FAST_L;
-    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    for (int i = lane; i < (1 << fast_bits); i += GW) fast[i] = 0;
     int rc = 0;
     if (lane == 0) {
         for (int i = 0; i < 16; i++) count[i] = 0;
@@ -103,10 +130,10 @@ __device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane)
             }
         }
     }
-    rc = __shfl_sync(0xffffffffu, rc, 0);
-    __syncwarp();
+    rc = __shfl_sync(gmask, rc, 0, GW);
+    __syncwarp(gmask);
     if (rc == 0 || rc == -2) {
-        for (int i = lane; i < n; i += 32) {
+        for (int i = lane; i < n; i += GW) {
             const int len = t.lens[base + i];
             if (len && len <= fast_bits) {
                 const uint32_t r = __brev((uint32_t)t.code_tmp[i]) >> (32 - len);
@@ -114,7 +141,7 @@ __device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane)
             }
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     return rc;
 }
 
@@ -122,7 +149,7 @@ __device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane)
 __device__ __forceinline__ int decode_sym(BitReader& b, const uint16_t* fast, int fast_bits, const uint16_t* count,
                                           const uint16_t* first, const uint16_t* offset, const uint16_t* sorted)
 {
-    b.refill();
+    if (b.nbits < 32) b.refill();
     const uint32_t e = fast[b.acc & ((1u << fast_bits) - 1)];
     if (e) {
         const int len = (int)(e & 15);
@@ -151,40 +178,53 @@ enum { OP_LIT = 0, OP_MATCH = 1, OP_EOB = 2, OP_ERR = 3 };
 
 __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflateParams P)
 {
-    __shared__ WarpTables tabs[INF_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpTables& t = tabs[warp];
+    __shared__ WarpTables tabs[INF_GROUPS];
+    const int lane = threadIdx.x % GW;   // lane within the group
+    const uint32_t gmask = GW >= 32 ? 0xffffffffu : ((1u << (GW & 31)) - 1u) << ((threadIdx.x & 31) - lane);
+    WarpTables& t = tabs[threadIdx.x / GW];
 
     for (;;) {
         uint32_t seg = 0;
         if (lane == 0) seg = atomicAdd(P.work_counter, 1u);
-        seg = __shfl_sync(0xffffffffu, seg, 0);
+        seg = __shfl_sync(gmask, seg, 0, GW);
         if (seg >= P.nseg) break;
 
         const uint64_t c_begin = seg == 0 ? P.first_offset : P.seg_end[seg - 1];
         const uint64_t c_end = P.seg_end[seg];
         const uint64_t o_begin = (uint64_t)seg * P.seg_size;
-        const uint64_t o_cap = (P.out_cap - o_begin) < P.seg_size ? (P.out_cap - o_begin) : P.seg_size;
+        const uint32_t o_cap = (uint32_t)((P.out_cap - o_begin) < P.seg_size ? (P.out_cap - o_begin) : P.seg_size);
         uint8_t* out = P.out + o_begin;
-        uint64_t o = 0;
+        uint32_t o = 0;
         int err = IE_OK;
+        uint32_t pend_at = 0;     // a short match copy whose loads are in flight (stores still to be issued)
+        int pend_len = 0;
+        uint8_t pend_val[PEND_PER_LANE] = {0};
         BitReader br;
-        br.in = P.in;
-        br.pos = c_begin;
-        br.end = c_end < P.n ? c_end : P.n;
+        br.in = P.in + c_begin;
+        br.pos = 0;
         br.acc = 0;
         br.nbits = 0;
-        if (c_end > P.n || c_begin > c_end) err = IE_TRUNCATED;
+        br.end = 0;
+        br.limit = 0;
+        if (c_end > P.n || c_begin > c_end || c_end - c_begin > 0xF0000000ull) err = IE_TRUNCATED;
+        else {
+            br.end = (uint32_t)(c_end - c_begin);
+            const uint64_t room = P.n - c_begin;
+            br.limit = room > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)room;
+        }
+        br.fast_end = br.limit >= 16 ? br.limit - 15 : 0;
 
         // blocks until the segment's compressed bytes are used up (it ends with the full-flush marker)
         while (err == IE_OK) {
             int hdr = -1;
             if (lane == 0) {
-                if (br.byte_pos() >= br.end && br.nbits < 8) hdr = -2;       // clean end of segment
+                const uint32_t used = br.byte_pos();
+                if (used > br.end) hdr = -3;            // ran past the segment's bytes
+                else if (used == br.end) hdr = -2;      // clean end of segment (after the byte-aligned full-flush marker)
                 else if (!br.need(3)) hdr = -3;
                 else { hdr = (int)br.peek(3); br.drop(3); }
             }
-            hdr = __shfl_sync(0xffffffffu, hdr, 0);
+            hdr = __shfl_sync(gmask, hdr, 0, GW);
             if (hdr == -2) break;
             if (hdr == -3) { err = IE_TRUNCATED; break; }
             const int type = hdr >> 1;   // BFINAL is ignored inside a segment: the stream's final block is the caller's
@@ -201,28 +241,32 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                         len = (((~nl) & 0xFFFF) == l) ? (int)l : -2;
                     }
                 }
-                len = __shfl_sync(0xffffffffu, len, 0);
+                len = __shfl_sync(gmask, len, 0, GW);
                 if (len == -1) { err = IE_TRUNCATED; break; }
                 if (len == -2) { err = IE_STORED_LEN; break; }
-                uint64_t src = 0;
-                if (lane == 0) src = br.byte_pos();
-                src = __shfl_sync(0xffffffffu, src, 0);
-                if (src + (uint64_t)len > br.end) { err = IE_TRUNCATED; break; }
-                if (o + (uint64_t)len > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
-                for (int i = lane; i < len; i += 32) out[o + i] = P.in[src + i];
-                o += (uint64_t)len;
-                if (lane == 0) { br.pos = src + (uint64_t)len; br.acc = 0; br.nbits = 0; }
-                __syncwarp();
+                uint32_t src = 0, send = 0;
+                if (lane == 0) { src = br.byte_pos(); send = br.end; }
+                src = __shfl_sync(gmask, src, 0, GW);
+                send = __shfl_sync(gmask, send, 0, GW);
+                if (src + (uint32_t)len > send) { err = IE_TRUNCATED; break; }
+                if (o + (uint32_t)len > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
+                {
+                    const uint8_t* sp = P.in + c_begin + src;
+                    for (int i = lane; i < len; i += GW) out[o + i] = sp[i];
+                }
+                o += (uint32_t)len;
+                if (lane == 0) { br.pos = src + (uint32_t)len; br.acc = 0; br.nbits = 0; }
+                __syncwarp(gmask);
                 continue;
             }
             if (type == 3) { err = IE_BLOCK_TYPE; break; }
             if (type == 1) {
                 // fixed tables (InfTree.cs:16-96)
-                for (int i = lane; i < 288; i += 32) t.lens[i] = (uint8_t)static_llen(i);
-                for (int i = lane; i < 30; i += 32) t.lens[288 + i] = 5;
-                __syncwarp();
-                build_table(t, 0, 288, false, lane);
-                build_table(t, 288, 30, true, lane);
+                for (int i = lane; i < 288; i += GW) t.lens[i] = (uint8_t)static_llen(i);
+                for (int i = lane; i < 30; i += GW) t.lens[288 + i] = 5;
+                __syncwarp(gmask);
+                build_table(t, 0, 288, false, lane, gmask);
+                build_table(t, 288, 30, true, lane, gmask);
             } else {
                 // dynamic header (InflateBlocks.cs:366-626)
                 int nl = 0, nd = 0, e = IE_OK;
@@ -244,13 +288,13 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                         }
                     }
                 }
-                e = __shfl_sync(0xffffffffu, e, 0);
+                e = __shfl_sync(gmask, e, 0, GW);
                 if (e != IE_OK) { err = e; break; }
-                nl = __shfl_sync(0xffffffffu, nl, 0);
-                nd = __shfl_sync(0xffffffffu, nd, 0);
-                __syncwarp();
+                nl = __shfl_sync(gmask, nl, 0, GW);
+                nd = __shfl_sync(gmask, nd, 0, GW);
+                __syncwarp(gmask);
                 // the bit-length code is decoded through the distance-table slots
-                int r = build_table(t, 0, 19, true, lane);
+                int r = build_table(t, 0, 19, true, lane, gmask);
                 if (r == -1) { err = IE_OVERSUB_BL; break; }
                 if (r != 0) { err = IE_INCOMPLETE_BL; break; }
                 if (lane == 0) {
@@ -273,70 +317,111 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                         }
                     }
                 }
-                e = __shfl_sync(0xffffffffu, e, 0);
+                e = __shfl_sync(gmask, e, 0, GW);
                 if (e != IE_OK) { err = e; break; }
-                __syncwarp();
-                r = build_table(t, 32, nl, false, lane);
+                __syncwarp(gmask);
+                r = build_table(t, 32, nl, false, lane, gmask);
                 if (r == -1) { err = IE_OVERSUB_L; break; }
                 if (r != 0) { err = IE_INCOMPLETE_L; break; }
-                r = build_table(t, 32 + nl, nd, true, lane);
+                r = build_table(t, 32 + nl, nd, true, lane, gmask);
                 if (r == -1) { err = IE_OVERSUB_D; break; }
                 if (r == -2) { err = IE_INCOMPLETE_D; break; }
                 if (r == 1 && nl > 257) { err = IE_EMPTY_D; break; }
             }
-            // ---- symbols (InfCodes.cs:106-817): lane 0 decodes, the warp copies matches ----
+            // ---- symbols (InfCodes.cs:106-817) ----
+            // Lane 0 decodes and stores literals on its own until it meets a match or the end of the block; the warp
+            // then copies the match.  A copy of <= PEND_MAX bytes is split: its loads are issued at once, its stores wait
+            // until the next match / end of block, so the L2 round trip of the back-reference hides behind the
+            // literals decoded in between (one copy in flight: the next match may read what this one writes).
             for (;;) {
-                int op = OP_ERR, a = 0, d = 0;
+                uint32_t packed = 0;   // op | len << 2 | dist << 12   (or op | error << 2)
+                uint32_t onow = 0;
                 if (lane == 0) {
-                    const int sym = decode_sym(br, t.fast_l, FAST_L, t.count_l, t.first_l, t.offset_l, t.sorted_l);
-                    if (sym == -2) { a = IE_TRUNCATED; }
-                    else if (sym < 0) { a = IE_BAD_LCODE; }
-                    else if (sym < 256) { op = OP_LIT; a = sym; }
-                    else if (sym == 256) { op = OP_EOB; }
-                    else if (sym - 257 >= 29) { a = IE_BAD_LCODE; }
-                    else {
+                    int op = OP_ERR, a = IE_BAD_LCODE, d = 0;
+                    for (;;) {
+                        if (br.nbits < 48) br.refill();
+                        uint32_t e = t.fast_l[br.acc & ((1u << FAST_L) - 1)];
+                        int sym;
+                        if (e) {
+                            br.drop((int)(e & 15));
+                            sym = (int)(e >> 4);
+                        } else {
+                            sym = decode_sym(br, t.fast_l, FAST_L, t.count_l, t.first_l, t.offset_l, t.sorted_l);
+                            if (sym < 0) { a = sym == -2 ? IE_TRUNCATED : IE_BAD_LCODE; break; }
+                        }
+                        if (sym < 256) {
+                            if (o >= o_cap) { a = IE_OUTPUT_OVERFLOW; break; }
+                            out[o++] = (uint8_t)sym;
+                            continue;
+                        }
+                        if (sym == 256) { op = OP_EOB; break; }
                         const int ls = sym - 257;
+                        if (ls >= 29) { a = IE_BAD_LCODE; break; }
                         int eb = c_len_extra[ls];
-                        if (!br.need(eb)) a = IE_TRUNCATED;
-                        else {
-                            const int len = c_len_base[ls] + (int)br.peek(eb);
-                            br.drop(eb);
-                            const int ds = decode_sym(br, t.fast_d, FAST_D, t.count_d, t.first_d, t.offset_d, t.sorted_d);
-                            if (ds == -2) a = IE_TRUNCATED;
-                            else if (ds < 0 || ds >= 30) a = IE_BAD_DCODE;
-                            else {
-                                eb = c_dist_extra[ds];
-                                if (!br.need(eb)) a = IE_TRUNCATED;
-                                else {
-                                    d = c_dist_base[ds] + (int)br.peek(eb);
-                                    br.drop(eb);
-                                    a = len;
-                                    op = OP_MATCH;
-                                }
-                            }
+                        const int len = c_len_base[ls] + (int)br.peek(eb);
+                        br.drop(eb);
+                        int ds;
+                        e = t.fast_d[br.acc & ((1u << FAST_D) - 1)];
+                        if (e) {
+                            br.drop((int)(e & 15));
+                            ds = (int)(e >> 4);
+                        } else {
+                            ds = decode_sym(br, t.fast_d, FAST_D, t.count_d, t.first_d, t.offset_d, t.sorted_d);
+                            if (ds < 0) { a = ds == -2 ? IE_TRUNCATED : IE_BAD_DCODE; break; }
+                        }
+                        if (ds >= 30) { a = IE_BAD_DCODE; break; }
+                        eb = c_dist_extra[ds];
+                        d = c_dist_base[ds] + (int)br.peek(eb);
+                        br.drop(eb);
+                        if (br.nbits < 0) { a = IE_TRUNCATED; break; }
+                        a = len;
+                        op = OP_MATCH;
+                        break;
+                    }
+                    if (op != OP_ERR && br.nbits < 0) { op = OP_ERR; a = IE_TRUNCATED; }
+                    packed = (uint32_t)op | ((uint32_t)a << 2) | ((uint32_t)d << 12);
+                    onow = o;
+                }
+                packed = __shfl_sync(gmask, packed, 0, GW);
+                o = __shfl_sync(gmask, onow, 0, GW);
+                const int op = (int)(packed & 3u);
+                // finish the copy in flight before anything else touches the output
+                if (pend_len) {
+#pragma unroll
+                    for (int j = 0; j < PEND_PER_LANE; j++) {
+                        const int i = lane + j * GW;
+                        if (i < pend_len) out[pend_at + i] = pend_val[j];
+                    }
+                    pend_len = 0;
+                }
+                __syncwarp(gmask);
+                if (op == OP_EOB) break;
+                if (op == OP_ERR) { err = (int)((packed >> 2) & 0x3ffu); break; }
+                const int a = (int)((packed >> 2) & 0x3ffu), d = (int)(packed >> 12);
+                if ((uint32_t)d > o) { err = IE_DIST_TOO_FAR; break; }
+                if (o + (uint32_t)a > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
+                // out[o + i] = out[o - d + (i mod d)]: every source byte was written before this match
+                if (a <= PEND_MAX) {
+#pragma unroll
+                    for (int j = 0; j < PEND_PER_LANE; j++) {
+                        const int i = lane + j * GW;
+                        if (i < a) {
+                            int k = i;
+                            if (k >= d) k %= d;   // overlapping copy (run): rare, so the division stays out of the common path
+                            pend_val[j] = __ldcg(out + (o - (uint32_t)d) + k);
                         }
                     }
-                    if (op == OP_LIT) {
-                        if (o < o_cap) out[o] = (uint8_t)a;
-                        else { op = OP_ERR; a = IE_OUTPUT_OVERFLOW; }
+                    pend_at = o;
+                    pend_len = a;
+                } else {
+                    for (int i = lane; i < a; i += GW) {
+                        int k = i;
+                        if (k >= d) k %= d;
+                        out[o + i] = __ldcg(out + (o - (uint32_t)d) + k);
                     }
+                    __syncwarp(gmask);
                 }
-                op = __shfl_sync(0xffffffffu, op, 0);
-                if (op == OP_LIT) { o++; continue; }
-                if (op == OP_EOB) break;
-                a = __shfl_sync(0xffffffffu, a, 0);
-                if (op == OP_ERR) { err = a; break; }
-                d = __shfl_sync(0xffffffffu, d, 0);
-                if ((uint64_t)d > o) { err = IE_DIST_TOO_FAR; break; }
-                if (o + (uint64_t)a > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
-                __syncwarp();
-                // out[o + i] = out[o - d + (i mod d)]: every source byte was written before this match
-                for (int i = lane; i < a; i += 32) {
-                    const int k = i < d ? i : i % d;
-                    out[o + i] = __ldcg(out + o - d + k);
-                }
-                o += (uint64_t)a;
-                __syncwarp();
+                o += (uint32_t)a;
             }
             if (err != IE_OK) break;
         }
@@ -346,15 +431,20 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
             P.seg_out_len[seg] = (uint32_t)o;
             P.seg_status[seg] = err;
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
 }
 
 cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream)
 {
     if (P.nseg == 0) return cudaSuccess;
-    int ctas = num_sms * 4;
-    const int need = (int)((P.nseg + INF_WARPS - 1) / INF_WARPS);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_segments_kernel, INF_THREADS, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+    }
+    int ctas = num_sms * per_sm;   // persistent: every resident warp pulls segments from the work counter
+    const int need = (int)((P.nseg + INF_GROUPS - 1) / INF_GROUPS);
     if (ctas > need) ctas = need;
     inflate_segments_kernel<<<ctas, INF_THREADS, 0, stream>>>(P);
     return cudaGetLastError();

@@ -42,6 +42,9 @@ struct Smem {
     uint32_t* batch_seq;
     uint16_t* tile_hh;   // TILE_MAX: what InsertString returned for each position of the current DeflateSlow tile
     uint2* tile_rec;     // TILE_MAX: Longest_match results of the tile (full / quarter chain budget)
+    uint32_t* fast_masks; // 2 * 8 ballots of the DeflateFast batch (per warp)
+    uint16_t* fast_endl;  // 64: next parse point of each batch position if it is one
+    uint16_t* fast_mst;   // 64: match start of each batch position
 };
 
 __device__ __forceinline__ uint32_t hash_of(const Smem& sm, uint32_t v, int hash_variant)
@@ -187,13 +190,6 @@ __device__ void fast_step(const Smem& sm, ParserState& s, const SegOut& o, const
     if (bflush) close_block(s, o);
 }
 
-__device__ __forceinline__ void bcast_state(ParserState& s)
-{
-    int* f = reinterpret_cast<int*>(&s);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(ParserState) / sizeof(int)); k++) f[k] = __shfl_sync(0xffffffffu, f[k], 0);
-}
-
 // Common prefix length of the window strings at p and c, capped at MAX_MATCH (what Longest_match's pre-filters plus
 // Compare256 amount to: a candidate replaces the best match iff this value exceeds best_len).
 __device__ __forceinline__ int common_prefix258(const uint8_t* win, int p, int c)
@@ -253,21 +249,32 @@ __device__ __forceinline__ int warp_extend_match(const uint8_t* win, int p, int 
     return len < MAX_MATCH ? len : MAX_MATCH;
 }
 
-// DeflateFast (Deflate.Fast.cs:20-128) by one warp: 32 consecutive positions are evaluated speculatively as parse
-// points (lane i = str_start + i) against the hash table as it stands before the batch; a ballot walk then resolves
-// the greedy parse, and the inserts of the positions the reference would have inserted are committed in position
-// order.  A position whose hash also occurs earlier in the same batch cannot be speculated on (its chain would start
-// inside the batch): when the parse reaches one, the batch ends there and the next one starts at it.  A position the
-// Q3 pre-insert touched (head[h] >= position) runs the reference iteration literally on lane 0.
-// "Occurs earlier in the batch" is decided through a small slot table (atomicMax of a batch-sequence | lane key per
-// hash slot; __match_any_sync costs ~12 cycles per distinct value on sm_100, 385 cycles for 32 hashes): a lane is
-// clean iff it is the first lane of the batch in its slot, which errs only towards "not clean".
+// DeflateFast (Deflate.Fast.cs:20-128) by FAST_WARPS warps: FAST_WARPS * 32 consecutive positions are evaluated
+// speculatively as parse points (thread i = str_start + i) against the hash table as it stands before the batch; a
+// mask walk then resolves the greedy parse, and the inserts of the positions the reference would have inserted are
+// committed in position order.  A position whose hash also occurs earlier in the same batch cannot be speculated on
+// (its chain would start inside the batch): when the parse reaches one, the batch ends there and the next one starts
+// at it.  A position the Q3 pre-insert touched (head[h] >= position) runs the reference iteration literally.
+// "Occurs earlier in the batch" is decided through a small slot table (atomicMax of a batch-sequence | index key per
+// hash slot; __match_any_sync costs ~12 cycles per distinct value on sm_100, 385 cycles for 32 hashes): a thread is
+// clean iff it is the first of the batch in its slot, which errs only towards "not clean".
+// The warps exchange six ballots and one u16 per position through shared memory and each of them runs the (uniform)
+// walk on its own, so three CTA-partial barriers per batch are all the synchronisation there is.
 // Runs until the window needs refilling / sliding or the segment is done.
-__device__ void parse_fast_warp(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
-                                int hash_variant, unsigned long long* stats)
+constexpr int FAST_WARPS = 2;
+constexpr int FAST_NB = FAST_WARPS * 32;
+
+__device__ __forceinline__ void fast_bar()
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t below = (1u << lane) - 1u;
+    if (FAST_WARPS == 1) __syncwarp();
+    else asm volatile("bar.sync 1, %0;" ::"n"(FAST_NB) : "memory");
+}
+
+__device__ void parse_fast_multi(const Smem& sm, ParserState& s, ParserState* shared_state, const SegOut& o,
+                                 const LevelCfg& cfg, int strategy, int hash_variant, unsigned long long* stats)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, idx = threadIdx.x;   // idx < FAST_NB
+    const uint64_t below = (1ull << idx) - 1ull;
     const bool quick = cfg.chain <= 4 && cfg.nice <= 16;  // level 1: the whole chain is probed in one round of loads
     long long st_t0 = 0, st_t1 = 0, st_t2 = 0, st_t3 = 0;
     uint32_t seq = *sm.batch_seq;
@@ -286,12 +293,12 @@ __device__ void parse_fast_warp(const Smem& sm, ParserState& s, const SegOut& o,
             nact = first_trigger - s.str_start;
             if (nact > s.lookahead) nact = s.lookahead;
         }
-        if (nact > 32) nact = 32;
+        if (nact > FAST_NB) nact = FAST_NB;
         if (nact > BLOCK_SYMS - s.last_lit) nact = BLOCK_SYMS - s.last_lit;
-        const uint32_t act = nact >= 32 ? 0xffffffffu : (1u << nact) - 1u;
+        const uint64_t act = nact >= 64 ? ~0ull : (1ull << nact) - 1ull;
 
         const int S = s.str_start, LA = s.lookahead;
-        const int p = S + lane, la = LA - lane;
+        const int p = S + idx, la = LA - idx;
         if (stats) st_t0 = clock64();
         // ---- speculative phase ----
         const bool hashed = la >= MIN_MATCH;
@@ -301,18 +308,19 @@ __device__ void parse_fast_warp(const Smem& sm, ParserState& s, const SegOut& o,
         lds16_unaligned(sm.win, p, scan);
         bool first_in_slot = true;
         seq++;
+        const uint32_t key = (seq << 6) | (uint32_t)(63 - idx);
         if (hashed) {
             h = hash_of(sm, __funnelshift_r(scan[0], scan[1], 16), hash_variant);
-            atomicMax(&sm.slot[h & SLOT_MASK], (seq << 5) | (uint32_t)(31 - lane));
+            atomicMax(&sm.slot[h & SLOT_MASK], key);
             c0 = sm.head[h];
         }
-        __syncwarp();
-        if (hashed) first_in_slot = sm.slot[h & SLOT_MASK] == ((seq << 5) | (uint32_t)(31 - lane));
+        fast_bar();
+        if (hashed) first_in_slot = sm.slot[h & SLOT_MASK] == key;
         const bool hard = hashed && c0 >= p;                 // Q2/Q3: the refill pre-inserted this position (or the next)
         const bool dirty = hashed && (!first_in_slot || hard);
         int best = MIN_MATCH - 1, mstart = 0;
         bool ext = false;  // best == 16 stands for "at least 16": the exact length is found if the position is a parse point
-        if (hashed && !dirty && lane < nact && c0 != 0 && p - c0 <= MAX_DIST && strategy != 2) {
+        if (hashed && !dirty && idx < nact && c0 != 0 && p - c0 <= MAX_DIST && strategy != 2) {
             const int nice = cfg.nice < la ? cfg.nice : la;
             const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
             if (quick) {
@@ -360,101 +368,122 @@ __device__ void parse_fast_warp(const Smem& sm, ParserState& s, const SegOut& o,
         }
         int len = best < la ? best : la;
         const bool is_match = len >= MIN_MATCH;
-        int endl = lane + (is_match ? len : 1);   // lane index of the next parse point if this lane is one
-        const uint32_t Mm = __ballot_sync(0xffffffffu, is_match) & act;
-        const uint32_t Dm = __ballot_sync(0xffffffffu, dirty) & act;
-        const uint32_t Xm = __ballot_sync(0xffffffffu, ext);
-        const uint32_t Hd = __ballot_sync(0xffffffffu, hard);
-        const uint32_t H3 = __ballot_sync(0xffffffffu, hashed);
-        if (stats) st_t1 = clock64();
-        // ---- resolve the greedy parse: hop from match to match, literals in between are parse points ----
-        int cur = 0;
-        uint32_t vis = 0;          // lanes whose match is taken
-        bool hit_dirty = false;
-        const uint32_t stops = Mm | Dm;
-        for (;;) {
-            const uint32_t stop = stops & (0xffffffffu << cur);
-            if (stop == 0) { cur = nact; break; }
-            const int nxt = __ffs(stop) - 1;
-            if ((Dm >> nxt) & 1u) { cur = nxt; hit_dirty = true; break; }
-            if ((Xm >> nxt) & 1u) {  // long match at a parse point: the warp finishes the compare
-                const int ms = __shfl_sync(0xffffffffu, mstart, nxt);
-                const int full = warp_extend_match(sm.win, S + nxt, ms, 16, lane);
-                if (lane == nxt) {
-                    len = full < la ? full : la;
-                    endl = lane + len;
-                }
+        {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, is_match), b1 = __ballot_sync(0xffffffffu, dirty);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, ext), b3 = __ballot_sync(0xffffffffu, hard);
+            const uint32_t b4 = __ballot_sync(0xffffffffu, hashed), b5 = __ballot_sync(0xffffffffu, first_in_slot && !hard);
+            if (lane == 0) {
+                uint32_t* m = sm.fast_masks + warp * 8;
+                m[0] = b0; m[1] = b1; m[2] = b2; m[3] = b3; m[4] = b4; m[5] = b5;
             }
-            vis |= 1u << nxt;
-            cur = __shfl_sync(0xffffffffu, endl, nxt);
+            sm.fast_endl[idx] = (uint16_t)(idx + (is_match ? len : 1));   // index of the next parse point if this is one
+            sm.fast_mst[idx] = (uint16_t)mstart;
+        }
+        fast_bar();
+        uint64_t Mm, Dm, Xm, Hd, H3, Fm;
+        {
+            const uint32_t* m = sm.fast_masks;
+            Mm = m[0]; Dm = m[1]; Xm = m[2]; Hd = m[3]; H3 = m[4]; Fm = m[5];
+            if (FAST_WARPS > 1) {
+                Mm |= (uint64_t)m[8] << 32; Dm |= (uint64_t)m[9] << 32; Xm |= (uint64_t)m[10] << 32;
+                Hd |= (uint64_t)m[11] << 32; H3 |= (uint64_t)m[12] << 32; Fm |= (uint64_t)m[13] << 32;
+            }
+            Mm &= act;
+            Dm &= act;
+        }
+        if (stats) st_t1 = clock64();
+        // ---- resolve the greedy parse (every warp on its own, the walk is uniform): hop from match to match; the
+        // literals in between are parse points; lanes under a taken match are not, but the interior of a short one
+        // is still inserted (Deflate.Fast.cs:81-104) ----
+        int cur = 0;
+        uint64_t vis = 0, cover = 0, shortins = 0;
+        int tail_last = 0;         // last interior position of a short match that runs past the batch
+        bool hit_dirty = false;
+        const uint64_t stops = Mm | Dm;
+        for (;;) {
+            const uint64_t stop = stops & (~0ull << cur);
+            if (stop == 0) { cur = nact; break; }
+            const int nxt = __ffsll((long long)stop) - 1;
+            if ((Dm >> nxt) & 1ull) { cur = nxt; hit_dirty = true; break; }
+            int e = sm.fast_endl[nxt];
+            if ((Xm >> nxt) & 1ull) {  // long match at a parse point: the warp finishes the compare
+                const int full = warp_extend_match(sm.win, S + nxt, sm.fast_mst[nxt], 16, lane);
+                const int lx = full < LA - nxt ? full : LA - nxt;
+                e = nxt + lx;
+                if (idx == nxt) len = lx;
+            }
+            const int mlen = e - nxt;
+            vis |= 1ull << nxt;
+            const uint64_t rng = (e >= 64 ? ~0ull : (1ull << e) - 1ull) & ~((2ull << nxt) - 1ull);
+            cover |= rng;
+            if (mlen <= cfg.lazy && LA - nxt - mlen >= MIN_MATCH) {
+                shortins |= rng;
+                if (e > FAST_NB) tail_last = S + e - 1;
+            }
+            cur = e;
             if (cur >= nact) break;
         }
-        // lanes covered by a taken match are not parse points; the interior of a short one is still inserted
-        const bool taken = (vis >> lane) & 1u;
-        const bool is_short = taken && len <= cfg.lazy && la - len >= MIN_MATCH;   // Deflate.Fast.cs:81
-        uint32_t cover = 0, shortins = 0;
-        if (taken) {
-            const uint32_t upto = endl >= 32 ? 0xffffffffu : (1u << endl) - 1u;
-            cover = upto & ~((2u << lane) - 1u);
-            if (is_short) shortins = cover;
-        }
-        cover = __reduce_or_sync(0xffffffffu, cover);
-        shortins = __reduce_or_sync(0xffffffffu, shortins);
-        const uint32_t tailm = __ballot_sync(0xffffffffu, is_short && endl > 32);
-        const uint32_t done_mask = cur >= 32 ? 0xffffffffu : (1u << cur) - 1u;
-        const uint32_t pm = done_mask & ~cover;              // parse points
-        const uint32_t im = (pm & H3) | shortins;            // inserted positions
+        const uint64_t done_mask = cur >= 64 ? ~0ull : (1ull << cur) - 1ull;
+        const uint64_t lanes_mask = FAST_NB >= 64 ? ~0ull : (1ull << FAST_NB) - 1ull;
+        const uint64_t pm = done_mask & ~cover & lanes_mask;             // parse points
+        const uint64_t im = ((pm & H3) | shortins) & lanes_mask;         // inserted positions
         if (stats) st_t2 = clock64();
         // ---- symbols (Tr_tally_*): parse points in position order ----
-        const int nsym = __popc(pm);
-        if ((pm >> lane) & 1u) {
-            const uint32_t v = taken ? ((uint32_t)(p - mstart) | ((uint32_t)(len - MIN_MATCH) << 16)) : ((scan[0] & 0xFFu) << 16);
-            o.sym[s.sym_total + __popc(pm & below)] = v;
+        const int nsym = __popcll(pm);
+        if ((pm >> idx) & 1ull) {
+            const uint32_t v = ((vis >> idx) & 1ull) ? ((uint32_t)(p - mstart) | ((uint32_t)(len - MIN_MATCH) << 16))
+                                                     : ((scan[0] & 0xFFu) << 16);
+            o.sym[s.sym_total + __popcll(pm & below)] = v;
         }
         // ---- commit InsertString of every inserted position, in position order ----
-        // Clean lanes are the only ones of their hash so far in the batch: they go first, side by side.  The others
-        // (a later lane of a hash already seen) follow one at a time, as the reference would execute them.
-        const uint32_t serial_ins = im & ~__ballot_sync(0xffffffffu, first_in_slot && !hard);
-        if (((im & ~serial_ins) >> lane) & 1u) {
+        // Threads that are the first of their hash slot go side by side.  The others (a later position of a slot already
+        // seen in the batch) follow one at a time, as the reference would execute them.
+        const uint64_t serial_ins = im & ~Fm;
+        if (((im & ~serial_ins) >> idx) & 1ull) {
             sm.prev[p & W_MASK] = (uint16_t)c0;
             sm.head[h] = (uint16_t)p;
         }
-        __syncwarp();
-        for (uint32_t m = serial_ins; m != 0; m &= m - 1) {
-            if (lane == __ffs(m) - 1) {
-                const int curh = sm.head[h];
-                if (curh != p) {   // Q2
-                    sm.prev[p & W_MASK] = (uint16_t)curh;
-                    sm.head[h] = (uint16_t)p;
+        if (serial_ins != 0) {
+            for (uint64_t m = serial_ins; m != 0; m &= m - 1) {
+                fast_bar();
+                if (idx == __ffsll((long long)m) - 1) {
+                    const int curh = sm.head[h];
+                    if (curh != p) {   // Q2
+                        sm.prev[p & W_MASK] = (uint16_t)curh;
+                        sm.head[h] = (uint16_t)p;
+                    }
                 }
             }
-            __syncwarp();
         }
         s.sym_total += nsym;
         s.last_lit += nsym;
         s.str_start = S + cur;
         s.lookahead = LA - cur;
         s.match_length = 0;
-        if (tailm != 0) {   // the interior of a short match runs past lane 31
-            const int last = S + __shfl_sync(0xffffffffu, endl, __ffs(tailm) - 1) - 1;
-            if (lane == 0)
-                for (int q = S + 32; q <= last; q++) insert_string(sm, q, hash_variant);
-            __syncwarp();
+        if (tail_last != 0) {   // the interior of a short match runs past the batch
+            fast_bar();
+            if (idx == 0)
+                for (int q = S + FAST_NB; q <= tail_last; q++) insert_string(sm, q, hash_variant);
         }
         if (s.last_lit == BLOCK_SYMS) {
             ParserState t = s;
-            if (lane == 0) close_block(t, o);
+            if (idx == 0) close_block(t, o);
             else { t.nblocks++; t.last_lit = 0; t.block_start = t.str_start; }
             s = t;
         }
         if (stats) st_t3 = clock64();
-        const bool serial = hit_dirty && ((Hd >> cur) & 1u);
+        const bool serial = hit_dirty && ((Hd >> cur) & 1ull);
+        fast_bar();   // the commits above are visible to every warp before the next batch reads head / prev
         if (serial) {
-            if (lane == 0) fast_step(sm, s, o, cfg, strategy, hash_variant);
-            bcast_state(s);
-            __syncwarp();
+            if (idx == 0) {
+                fast_step(sm, s, o, cfg, strategy, hash_variant);
+                *shared_state = s;
+            }
+            fast_bar();
+            s = *shared_state;
+            fast_bar();
         }
-        if (stats && lane == 0) {
+        if (stats && idx == 0) {
             const long long t4 = clock64();
             atomicAdd(stats + 0, 1ull);
             atomicAdd(stats + 1, (unsigned long long)cur);
@@ -464,16 +493,16 @@ __device__ void parse_fast_warp(const Smem& sm, ParserState& s, const SegOut& o,
             atomicAdd(stats + 5, (unsigned long long)(st_t2 - st_t1));
             atomicAdd(stats + 6, (unsigned long long)(st_t3 - st_t2));
             atomicAdd(stats + 7, (unsigned long long)(t4 - st_t3));
-            atomicAdd(stats + 8, (unsigned long long)__popc(vis));
-            atomicAdd(stats + 9, (unsigned long long)__popc(Dm));
-            atomicAdd(stats + 12, (unsigned long long)__popc(Xm & vis));
+            atomicAdd(stats + 8, (unsigned long long)__popcll(vis));
+            atomicAdd(stats + 9, (unsigned long long)__popcll(Dm));
+            atomicAdd(stats + 12, (unsigned long long)__popcll(Xm & vis));
             atomicAdd(stats + 13, serial ? 1ull : 0ull);
-            atomicAdd(stats + 14, (unsigned long long)__popc(serial_ins));
+            atomicAdd(stats + 14, (unsigned long long)__popcll(serial_ins));
         }
     }
-    if (lane == 0) *sm.batch_seq = seq;
+    if (idx == 0) *sm.batch_seq = seq;
     if (s.done) {
-        if (lane == 0) close_block(s, o);  // the end-of-input Flush_block_only(false) (Deflate.Fast.cs:124)
+        if (idx == 0) close_block(s, o);  // the end-of-input Flush_block_only(false) (Deflate.Fast.cs:124)
         else { s.nblocks++; s.last_lit = 0; s.block_start = s.str_start; }
     }
 }
@@ -827,7 +856,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
     sm.tile_rec = reinterpret_cast<uint2*>(red + 64);
     sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + TILE_MAX);
     sm.tile_hh = reinterpret_cast<uint16_t*>(sm.slot + SLOT_COUNT);
-    ParserState* shared_state = reinterpret_cast<ParserState*>(sm.tile_hh + TILE_MAX);
+    sm.fast_masks = reinterpret_cast<uint32_t*>(sm.tile_hh + TILE_MAX);
+    sm.fast_endl = reinterpret_cast<uint16_t*>(sm.fast_masks + 16);
+    sm.fast_mst = sm.fast_endl + 64;
+    ParserState* shared_state = reinterpret_cast<ParserState*>(sm.fast_mst + 64);
     int* seg_slot = reinterpret_cast<int*>(shared_state + 1);
     sm.batch_seq = reinterpret_cast<uint32_t*>(seg_slot + 1);
 
@@ -969,11 +1001,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
             const long long st_f1 = P.stats ? clock64() : 0;
             // ---- parse until the next refill / slide or the end of the segment ----
             if (cfg.fn == FN_FAST) {
-                if (tid < 32) {
+                if (tid < FAST_NB) {
                     ParserState s = *shared_state;
-                    __syncwarp();
-                    parse_fast_warp(sm, s, o, cfg, P.strategy, P.hash_variant, P.stats);
-                    __syncwarp();
+                    fast_bar();
+                    parse_fast_multi(sm, s, shared_state, o, cfg, P.strategy, P.hash_variant, P.stats);
+                    fast_bar();
                     if (tid == 0) *shared_state = s;
                 }
             } else if (cfg.fn == FN_SLOW) {
@@ -1034,7 +1066,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
 
 size_t lz77_smem_bytes()
 {
-    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 256 * 8 + 256 * 2;
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 256 * 8 + 256 * 2 + 64 + 128 + 128;
 }
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)

@@ -649,11 +649,11 @@ __device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const Le
 
 // (C): DeflateSlow (Deflate.Slow.cs:18-159) over the tile [S, S + T), Longest_match / InsertString looked up.
 __device__ void slow_tile_replay(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
-                                 int hash_variant, int S, int T)
+                                 int hash_variant, int S, int T, int until)
 {
     const int tile_end = S + T;
     int hash_head = 0;
-    while (s.str_start < tile_end) {
+    while (s.str_start < until) {
         const int idx = s.str_start - S;
         hash_head = sm.tile_hh[idx];
         s.prev_length = s.match_length;
@@ -696,6 +696,127 @@ __device__ void slow_tile_replay(const Smem& sm, ParserState& s, const SegOut& o
             s.str_start++;
             s.lookahead--;
         }
+    }
+}
+
+__device__ __forceinline__ void bcast_state(ParserState& s)
+{
+    int* f = reinterpret_cast<int*>(&s);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(ParserState) / sizeof(int)); k++) f[k] = __shfl_sync(0xffffffffu, f[k], 0);
+}
+
+// (C) by one warp: the DeflateSlow state machine (Deflate.Slow.cs:40-146) over 32 positions at a time, lane = one visit
+// (one loop iteration of the reference).  While no match is pending (match_length == 2) every position whose search
+// finds nothing just emits the previous byte as a literal, so those runs are taken in one step with a ballot; around a
+// match the lazy evaluation is stepped visit by visit, each lane looking up its own Longest_match result for the
+// pending prev_length.  Every visit emits at most one symbol: they are stored in lane order.
+__device__ void slow_tile_replay_warp(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
+                                      int hash_variant, int S, int T)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t below = (1u << lane) - 1u;
+    const int tile_end = S + T;
+    int ins_done_to = tile_end;   // positions >= tile_end below this one have been inserted
+    while (s.str_start < tile_end) {
+        const int g0 = s.str_start;
+        const int gn = tile_end - g0 < 32 ? tile_end - g0 : 32;
+        if (s.last_lit + 32 >= BLOCK_SYMS) {   // a block ends inside this stretch: the reference loop, literally
+            if (lane == 0) slow_tile_replay(sm, s, o, cfg, strategy, hash_variant, S, T, g0 + gn);
+            bcast_state(s);
+            if (s.str_start > ins_done_to) ins_done_to = s.str_start;
+            continue;
+        }
+        const int p = g0 + lane;
+        const bool valid = lane < gn;
+        int hh = 0;
+        uint32_t full = MIN_MATCH - 1, early = MIN_MATCH - 1;
+        if (valid) {
+            hh = sm.tile_hh[p - S];
+            const uint2 r = sm.tile_rec[p - S];
+            full = r.x;
+            early = r.y;
+        }
+        const uint32_t prev_byte = p > 0 ? sm.win[p - 1] : 0u;
+        const bool searchable = valid && hh != 0 && p - hh <= MAX_DIST && strategy != 2;
+        const int fullL = (int)(full & 511u), fullMs = (int)(full >> 9);
+        // what the visit yields when nothing is pending (prev_length == 2)
+        int D = MIN_MATCH - 1;
+        if (searchable && fullL > D) {
+            D = fullL;
+            if (D <= 5 && (strategy == 1 || (D == MIN_MATCH && p - fullMs > 4096))) D = MIN_MATCH - 1;
+        }
+        const uint32_t NQ = __ballot_sync(0xffffffffu, D >= MIN_MATCH);
+        uint32_t litmask = 0, matmask = 0;
+        int my_len = 0, my_dist = 0;
+        int cur = 0;
+        int mlp = s.match_length, msp = s.match_start, avail = s.match_available;
+        while (cur < gn) {
+            if (mlp < MIN_MATCH) {
+                const uint32_t rem = NQ & (0xffffffffu << cur);
+                const int nxt = rem ? __ffs(rem) - 1 : gn;
+                if (nxt > cur) {   // visits cur .. nxt-1 find nothing: literals of the bytes before them
+                    uint32_t run = (nxt >= 32 ? 0xffffffffu : (1u << nxt) - 1u) & (0xffffffffu << cur);
+                    if (!avail) run &= ~(1u << cur);
+                    litmask |= run;
+                    avail = 1;
+                }
+                if (nxt >= gn) { cur = gn; break; }
+                if (avail) litmask |= 1u << nxt;
+                avail = 1;
+                mlp = __shfl_sync(0xffffffffu, D, nxt);
+                msp = __shfl_sync(0xffffffffu, fullMs, nxt);
+                cur = nxt + 1;
+            } else {
+                // visit `cur` with prev_length = mlp pending: Longest_match from best_len = prev_length, chain >> 2 if >= good
+                int ml = MIN_MATCH - 1, msn = msp;
+                if (searchable && mlp < cfg.lazy) {
+                    const uint32_t e = mlp >= cfg.good ? early : full;
+                    int best = mlp;
+                    if ((int)(e & 511u) > best) {
+                        best = (int)(e & 511u);
+                        msn = (int)(e >> 9);
+                    }
+                    ml = best;
+                    if (ml <= 5 && (strategy == 1 || (ml == MIN_MATCH && p - msn > 4096))) ml = MIN_MATCH - 1;
+                }
+                const int ml_c = __shfl_sync(0xffffffffu, ml, cur);
+                const int ms_c = __shfl_sync(0xffffffffu, msn, cur);
+                if (ml_c <= mlp) {   // the pending match stands: emitted at this visit, the parse skips to its end
+                    matmask |= 1u << cur;
+                    if (lane == cur) {
+                        my_len = mlp;
+                        my_dist = (g0 + cur - 1) - msp;
+                    }
+                    cur += mlp - 1;
+                    avail = 0;
+                    mlp = MIN_MATCH - 1;
+                } else {
+                    litmask |= 1u << cur;
+                    mlp = ml_c;
+                    cur++;
+                }
+                msp = ms_c;
+            }
+        }
+        const uint32_t emit = litmask | matmask;
+        if ((emit >> lane) & 1u) {
+            const uint32_t v = ((matmask >> lane) & 1u) ? ((uint32_t)my_dist | ((uint32_t)(my_len - MIN_MATCH) << 16)) : (prev_byte << 16);
+            o.sym[s.sym_total + __popc(emit & below)] = v;
+        }
+        const int nsym = __popc(emit);
+        s.sym_total += nsym;
+        s.last_lit += nsym;
+        s.str_start = g0 + cur;
+        s.lookahead -= cur;
+        s.match_length = mlp;
+        s.match_start = msp;
+        s.match_available = avail;
+    }
+    if (s.str_start > ins_done_to) {   // positions past the tile that the last match skipped over (Deflate.Slow.cs:98-105)
+        if (lane == 0)
+            for (int q = ins_done_to; q < s.str_start; q++) insert_string(sm, q, hash_variant);
+        __syncwarp();
     }
 }
 
@@ -1029,10 +1150,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                     if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
                     __syncthreads();
                     const long long tC = P.stats ? clock64() : 0;
-                    if (tid == 0) {
+                    if (tid < 32) {
                         ParserState s = *shared_state;
-                        slow_tile_replay(sm, s, o, cfg, P.strategy, P.hash_variant, S, T);
-                        *shared_state = s;
+                        __syncwarp();
+                        slow_tile_replay_warp(sm, s, o, cfg, P.strategy, P.hash_variant, S, T);
+                        __syncwarp();
+                        if (tid == 0) *shared_state = s;
                     }
                     __syncthreads();
                     if (P.stats && tid == 0) {

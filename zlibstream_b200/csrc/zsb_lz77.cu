@@ -1144,11 +1144,16 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                         break;
                     }
                     const long long tA = P.stats ? clock64() : 0;
-                    if (tid < 32) slow_tile_insert(sm, S, T, P.hash_variant);
-                    __syncthreads();
+                    // HuffmanOnly never searches (Deflate.Slow.cs:66) and the hash table cannot reach the output: replay only
+                    if (P.strategy != 2) {
+                        if (tid < 32) slow_tile_insert(sm, S, T, P.hash_variant);
+                        __syncthreads();
+                    }
                     const long long tB = P.stats ? clock64() : 0;
-                    if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
-                    __syncthreads();
+                    if (P.strategy != 2) {
+                        if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
+                        __syncthreads();
+                    }
                     const long long tC = P.stats ? clock64() : 0;
                     if (tid < 32) {
                         ParserState s = *shared_state;

@@ -16,8 +16,8 @@ import torch  # noqa: E402
 import synth  # noqa: E402
 from zlibstream_b200 import Engine  # noqa: E402
 
-NAMES = ["batches", "consumed", "dirty_stops", "nact_sum", "cyc_spec", "cyc_resolve", "cyc_emit_commit", "cyc_serial",
-         "matches", "dirty_lanes", "cyc_fill", "cyc_parse", "slow_positions", "slow_serial", "x14", "x15"]
+NAMES = ["batches", "consumed", "dirty_stops", "nact_sum", "cyc_spec_links", "cyc_rounds", "x6", "x7",
+         "matches", "x9", "cyc_fill", "cyc_parse", "x12", "x13", "serial_inserts", "rounds"]
 
 
 def main():

@@ -954,6 +954,11 @@ static const char* const k_errmsg[10] = {"need dictionary", "stream end", "", "f
                                          "data error", "insufficient memory", "buffer error", "incompatible version", ""};
 #define ERRMSG(code) k_errmsg[ZSO_NEED_DICT - (code)]
 
+/* Test-only hook: tools/fc_model/fc_model.c includes this file and swaps in an experimental DeflateFast to check
+ * that a restructured parse (the one the CUDA kernel uses) is equivalent to the literal one below.  Always NULL in
+ * libzso.so. */
+static int (*g_fast_hook)(zso_deflater* s, int flush);
+
 static int deflate_call(zso_deflater* s, int flush)
 {
     if (flush > ZSO_FINISH || flush < 0) return ZSO_STREAM_ERROR;
@@ -1000,7 +1005,7 @@ static int deflate_call(zso_deflater* s, int flush)
         int bstate;
         if (s->strategy == ZSO_RLE) bstate = deflate_rle(s, flush);
         else if (k_cfg[s->level].fn == FN_STORED) bstate = deflate_stored(s, flush);
-        else if (k_cfg[s->level].fn == FN_FAST) bstate = deflate_fast(s, flush);
+        else if (k_cfg[s->level].fn == FN_FAST) bstate = g_fast_hook ? g_fast_hook(s, flush) : deflate_fast(s, flush);
         else bstate = deflate_slow(s, flush);
         if (bstate == BS_FINISH_STARTED || bstate == BS_FINISH_DONE) s->status = ST_FINISH;
         if (bstate == BS_NEED_MORE || bstate == BS_FINISH_STARTED) {

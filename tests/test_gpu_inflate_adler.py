@@ -29,13 +29,24 @@ def test_adler32_worst_case_bytes(engine):
 
 
 @pytest.mark.parametrize("level,strategy,ss", [(1, 0, 65536), (6, 0, 65536), (9, 0, 262144), (6, 1, 65536), (6, 2, 65536),
-                                               (1, 4, 65536), (3, 0, 131072)])
+                                               (1, 4, 65536), (3, 0, 131072), (6, 3, 65536)])
 def test_inflate_reference_streams(engine, oracle, corpus, level, strategy, ss):
     """Streams produced by the oracle (= the reference's bytes): decoded bytes and Adler-32 must be exact."""
     data = b"".join(corpus[k] for k in sorted(corpus))
     comp, ends, adler = oracle.deflate_segments(data, ss, level, strategy)
     out, ad = engine.inflate_segments(comp, ends, ss, len(data))
     assert out == data and ad == adler == zlib.adler32(data)
+
+
+def test_inflate_rle_carry_and_mixed(engine, oracle):
+    """Q14: Rle segments may open with a run of the previous segment's last byte (whole segments of it for zeros);
+    mixed-entropy tiles exercise stored blocks, long runs and long codes side by side in one warp."""
+    for data, level, strategy, ss in ((bytes(400000), 6, 3, 65536), (corpus_data.png_like(700000, seed=3), 6, 3, 65536),
+                                      (corpus_data.mixed_entropy(5 * 262144 + 77, seed=2), 6, 0, 262144),
+                                      (corpus_data.mixed_entropy(9 * 65536 + 5, seed=4), 1, 0, 65536)):
+        comp, ends, adler = oracle.deflate_segments(data, ss, level, strategy)
+        out, ad = engine.inflate_segments(comp, ends, ss, len(data))
+        assert out == data and ad == adler == zlib.adler32(data)
 
 
 def test_inflate_stored_and_degenerate(engine, oracle):

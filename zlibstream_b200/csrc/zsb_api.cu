@@ -73,7 +73,7 @@ struct zsb_ctx {
     std::string err;
     uint64_t launches = 0;
     // scratch
-    DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status;
+    DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry;
     uint16_t* crc_tab = nullptr;
     unsigned long long* lz_stats = nullptr;  // 32 counters, only with ZSB_LZ_STATS=1
     // timing of the last call
@@ -220,7 +220,7 @@ void zsb_ctx_destroy(zsb_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     DevBuf* bufs[] = {&ctx->in_stage, &ctx->out_stage, &ctx->sym, &ctx->blocks, &ctx->nblocks, &ctx->codes, &ctx->layout,
-                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status};
+                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status, &ctx->inf_scratch, &ctx->inf_carry};
     for (DevBuf* b : bufs) b->release();
     if (ctx->crc_tab) cudaFree(ctx->crc_tab);
     if (ctx->lz_stats) cudaFree(ctx->lz_stats);
@@ -493,7 +493,17 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     uint8_t* small = ctx->small.as<uint8_t>();
     uint32_t* d_adler = reinterpret_cast<uint32_t*>(small + 12);
     unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
-    CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    unsigned int* d_carry_flag = reinterpret_cast<unsigned int*>(small + 20);
+    CU(cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned int), st));
+    // ZSB_INFLATE_KERNEL=warp selects the older warp-per-segment kernel (A/B measurements); default: lane per segment
+    static const bool use_lanes = [] {
+        const char* e = getenv("ZSB_INFLATE_KERNEL");
+        return !(e && strcmp(e, "warp") == 0);
+    }();
+    if (use_lanes) {
+        CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
+        CU(ctx->inf_carry.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
+    }
 
     InflateParams I;
     I.in = d_in;
@@ -508,14 +518,21 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     I.seg_adler = nullptr;
     I.seg_status = ctx->inf_status.as<int>();
     I.work_counter = d_work;
+    if (use_lanes) {
+        I.seg_carry = ctx->inf_carry.as<uint32_t>();
+        I.carry_flag = d_carry_flag;
+    }
     timing_mark(ctx, 2, true);
-    CU(launch_inflate(I, ctx->num_sms, st));
+    if (use_lanes) CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+    else CU(launch_inflate(I, ctx->num_sms, st));
     timing_mark(ctx, 2, false);
     ctx->launches++;
     std::vector<int> status(nseg);
     std::vector<uint32_t> lens(nseg);
     uint32_t got_adler = 1;
     uint8_t trailer[6] = {0};
+    unsigned int carry_flag = 0;
+    if (use_lanes) CU(cudaMemcpyAsync(&carry_flag, d_carry_flag, sizeof carry_flag, cudaMemcpyDeviceToHost, st));
     if (nseg) {
         CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -535,6 +552,10 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         produced += lens[k];
     }
     if (out_len) *out_len = produced;
+    if (carry_flag) {   // Q14: Rle segments that open with a run of the previous segment's last byte
+        CU(launch_inflate_carry_fixup(I, st));
+        ctx->launches++;
+    }
     // running Adler-32 of the output (InflateBlocks.cs:755,792) as a separate pass over the decoded bytes
     CU(launch_adler32(d_out, produced, 1u, ctx->seg_adler.as<uint2>(), (uint32_t)(achunks ? achunks : 1), d_adler, st));
     ctx->launches += 2;

@@ -94,8 +94,15 @@ struct InflateParams {
     uint2* seg_adler;          // [nseg]
     int* seg_status;           // [nseg] 0 ok, else error id
     unsigned int* work_counter;
+    uint32_t* seg_carry = nullptr;   // [nseg] Q14: leading bytes that repeat the previous segment's last byte (lane kernel)
+    unsigned int* carry_flag = nullptr;   // set to 1 if any seg_carry is non-zero
 };
 cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream);
+// Lane-per-segment kernel (zsb_inflate_lanes.cu): the default.  scratch: inflate_lanes_scratch_bytes(num_sms) bytes.
+size_t inflate_lanes_scratch_bytes(int num_sms);
+cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream);
+// Q14 fix-up after the lane kernel: fills the carried leading bytes of Rle segments.
+cudaError_t launch_inflate_carry_fixup(const InflateParams& P, cudaStream_t stream);
 // Scans `in` for full-flush markers and validates them into a segment index (device side).
 cudaError_t launch_index_markers(const uint8_t* in, size_t n, uint64_t first_offset, uint64_t* cand, uint32_t cand_cap,
                                  uint32_t* ncand, cudaStream_t stream);

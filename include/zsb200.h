@@ -125,6 +125,21 @@ ZSB_API int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const u
                                  size_t nseg, size_t seg_size, unsigned flags, void* out, size_t out_cap,
                                  size_t* out_len, uint32_t* adler);
 
+/*
+ * Segment index of a full-flush-segmented stream that comes without a side-car, e.g. one written by the reference itself
+ * (SURVEY.md section 8f-1).  The reference's own resynchronisation primitive is InflateSync (Inflate.cs:386-448), which
+ * looks for the same 00 00 FF FF marker one flush point at a time.  Candidates are validated by decoding (chance
+ * occurrences of the pattern inside stored or Huffman data are merged away) and the repeated markers of Q10 are kept with
+ * the segment they follow.
+ *
+ *   seg_end_offsets, cap   receives the end offset of every segment (may be NULL to query the count only)
+ *   nseg                   number of segments found
+ *   uncompressed_size      total decoded size (every segment but the last is seg_size bytes)
+ *   flags                  ZSB_IN_DEVICE, ZSB_OFFSETS_DEVICE, ZSB_NO_HEADER, ZSB_NO_TRAILER
+ */
+ZSB_API int zsb_build_segment_index(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size, unsigned flags,
+                                    uint64_t* seg_end_offsets, size_t cap, size_t* nseg, uint64_t* uncompressed_size);
+
 /* Replaces Adler32.Calculate(adler, span) (Adler32.cs:51-78). flags: ZSB_IN_DEVICE. */
 ZSB_API int zsb_adler32(zsb_ctx* ctx, uint32_t seed, const void* p, size_t n, unsigned flags, uint32_t* result);
 /* adler32_combine; absent from the reference. Pure host function. */

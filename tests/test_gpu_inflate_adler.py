@@ -49,6 +49,42 @@ def test_inflate_rle_carry_and_mixed(engine, oracle):
         assert out == data and ad == adler == zlib.adler32(data)
 
 
+@pytest.mark.parametrize("level,strategy,ss", [(1, 0, 65536), (6, 0, 65536), (9, 0, 262144), (6, 2, 65536), (6, 3, 65536)])
+def test_inflate_without_side_car(engine, oracle, corpus, level, strategy, ss):
+    """a stream written by the reference has no segment offsets; the index is rebuilt from the full-flush
+    markers (and must reproduce the reference's segment end offsets, i.e. ZlibOutputStream.TotalOut after each Write)."""
+    data = b"".join(corpus[k] for k in sorted(corpus))
+    comp, ends, adler = oracle.deflate_segments(data, ss, level, strategy)
+    got_ends, total = engine.build_segment_index(comp, ss)
+    assert got_ends == ends and total == len(data)
+    out, ad = engine.inflate_segments(comp, None, ss, len(data))
+    assert out == data and ad == adler
+
+
+def test_index_scan_tolerates_chance_markers(engine, oracle):
+    """00 00 FF FF inside stored blocks (verbatim input) and next to real markers must not split a segment."""
+    rng = np.random.RandomState(11)
+    raw = bytearray(rng.bytes(4 * 65536 + 999))
+    for pos in (5, 1000, 65530, 65534, 65536, 70000, 131072 - 4, 200000, 262144 + 10, len(raw) - 4):
+        raw[pos:pos + 4] = b"\x00\x00\xff\xff"
+    text = corpus_data.text_like(3 * 65536, seed=5)
+    for data in (bytes(raw), text[:65536] + bytes(raw[:65536]) + text[65536:] + b"\x00\x00\xff\xff" * 64):
+        comp, ends, adler = oracle.deflate_segments(data, 65536, 6)
+        assert comp.count(b"\x00\x00\xff\xff") > len(ends)
+        got_ends, total = engine.build_segment_index(comp, 65536)
+        assert got_ends == ends and total == len(data)
+        out, ad = engine.inflate_segments(comp, None, 65536, len(data))
+        assert out == data and ad == adler
+
+
+def test_input_stream_without_offsets(engine, oracle, corpus):
+    from zlibstream_b200 import ZlibInputStream
+    data = corpus["alice29.txt"] + corpus["kennedy.xls"]
+    comp, ends, adler = oracle.deflate_segments(data, 65536, 6)
+    zi = ZlibInputStream(io.BytesIO(comp), segment_size=65536, engine=engine)
+    assert zi.read() == data and zi.Adler == adler
+
+
 def test_inflate_stored_and_degenerate(engine, oracle):
     rng = np.random.RandomState(3)
     for data in (rng.bytes(300001), bytes(400000), b"a", corpus_data.sparse_image(256, 300)):

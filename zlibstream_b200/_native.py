@@ -15,7 +15,7 @@ ZSB_OFFSETS_DEVICE = 0x10
 EXPORTS = [
     "zsb_ctx_create", "zsb_ctx_destroy", "zsb_last_error", "zsb_ctx_set_stream", "zsb_ctx_get_stream",
     "zsb_ctx_launch_count", "zsb_ctx_last_kernel_ms", "zsb_deflate_bound", "zsb_deflate_segments",
-    "zsb_inflate_segments", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
+    "zsb_inflate_segments", "zsb_build_segment_index", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
 ]
 
 _lib = None
@@ -58,6 +58,8 @@ def load():
     lib.zsb_deflate_segments.restype = i32
     lib.zsb_inflate_segments.argtypes = [vp, vp, sz, vp, sz, sz, c.c_uint, vp, sz, c.POINTER(sz), c.POINTER(u32)]
     lib.zsb_inflate_segments.restype = i32
+    lib.zsb_build_segment_index.argtypes = [vp, vp, sz, sz, c.c_uint, vp, sz, c.POINTER(sz), c.POINTER(u64)]
+    lib.zsb_build_segment_index.restype = i32
     lib.zsb_adler32.argtypes = [vp, u32, vp, sz, c.c_uint, c.POINTER(u32)]
     lib.zsb_adler32.restype = i32
     lib.zsb_adler32_combine.argtypes = [u32, u32, u64]

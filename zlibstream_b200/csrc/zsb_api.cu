@@ -5,6 +5,7 @@
 #include "../../include/zsb200.h"
 #include "zsb_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -73,7 +74,7 @@ struct zsb_ctx {
     std::string err;
     uint64_t launches = 0;
     // scratch
-    DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry;
+    DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry, idx_cand;
     uint16_t* crc_tab = nullptr;
     unsigned long long* lz_stats = nullptr;  // 32 counters, only with ZSB_LZ_STATS=1
     // timing of the last call
@@ -178,6 +179,109 @@ size_t env_size(const char* name, size_t dflt)
 
 }  // namespace
 
+namespace {
+
+// Segment index of a stream that comes without a side-car (the reference's own resynchronisation is
+// InflateSync, Inflate.cs:386-448).  Candidates = every 00 00 FF FF in the body; the pieces between consecutive candidates
+// are decoded in count-only mode; a piece that does not decode is a chance occurrence of the pattern (inside a stored
+// block or inside Huffman data) and is merged with its successor; pieces are then grouped into segments of seg_size
+// bytes -- zero-length pieces (the repeated markers of Q10) stay with the segment they follow.
+int build_segment_index(zsb_ctx* ctx, const uint8_t* d_in, size_t n, uint64_t first, uint64_t body_end, size_t seg_size,
+                        std::vector<uint64_t>& ends, uint64_t* total_bytes = nullptr)
+{
+    ends.clear();
+    if (total_bytes) *total_bytes = 0;
+    if (body_end <= first) return ZSB_OK;
+    cudaStream_t st = ctx->stream;
+    const size_t cap = std::max<size_t>(1u << 20, (body_end - first) / 64 + 1024);
+    CU(ctx->idx_cand.reserve(cap * sizeof(uint64_t)));
+    uint8_t* small = ctx->small.as<uint8_t>();
+    uint32_t* d_ncand = reinterpret_cast<uint32_t*>(small + 24);
+    unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
+    CU(cudaMemsetAsync(d_ncand, 0, sizeof(uint32_t), st));
+    CU(launch_index_markers(d_in, first, body_end, ctx->idx_cand.as<uint64_t>(), (uint32_t)std::min<size_t>(cap, 0xFFFFFFFFu), d_ncand, st));
+    ctx->launches++;
+    uint32_t ncand = 0;
+    CU(cudaMemcpyAsync(&ncand, d_ncand, sizeof ncand, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ncand > cap) return fail(ctx, ZSB_DATA_ERROR, "too many full-flush marker candidates");
+    std::vector<uint64_t> cand(ncand);
+    if (ncand) CU(cudaMemcpyAsync(cand.data(), ctx->idx_cand.p, ncand * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::sort(cand.begin(), cand.end());
+    if (cand.empty() || cand.back() != body_end) return fail(ctx, ZSB_DATA_ERROR, "stream does not end with a full-flush marker");
+    CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
+    std::vector<int> status;
+    std::vector<uint32_t> lens;
+    for (int pass = 0;; pass++) {
+        const size_t np = cand.size();
+        CU(ctx->seg_end.reserve(np * sizeof(uint64_t)));
+        CU(ctx->inf_len.reserve(np * sizeof(uint32_t)));
+        CU(ctx->inf_status.reserve(np * sizeof(int)));
+        CU(cudaMemcpyAsync(ctx->seg_end.p, cand.data(), np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+        InflateParams I;
+        I.in = d_in;
+        I.n = n;
+        I.seg_end = ctx->seg_end.as<uint64_t>();
+        I.first_offset = first;
+        I.nseg = (uint32_t)np;
+        I.seg_size = 0;
+        I.out = nullptr;
+        I.out_cap = 0;
+        I.seg_out_len = ctx->inf_len.as<uint32_t>();
+        I.seg_adler = nullptr;
+        I.seg_status = ctx->inf_status.as<int>();
+        I.work_counter = d_work;
+        I.count_only = 1;
+        CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+        ctx->launches++;
+        status.resize(np);
+        lens.resize(np);
+        CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, np * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<uint64_t> kept;
+        kept.reserve(np);
+        bool any_bad = false;
+        for (size_t i = 0; i < np; i++) {
+            if (status[i] == IE_OK) {
+                kept.push_back(cand[i]);
+                continue;
+            }
+            any_bad = true;
+            if (i + 1 == np || pass >= 8) {   // nothing left to merge with: the data really is damaged
+                int e = status[i];
+                if (e < 0 || e > IE_SEG_SIZE) e = IE_TRUNCATED;
+                return fail(ctx, (e == IE_TRUNCATED || e == IE_OUTPUT_OVERFLOW) ? ZSB_BUF_ERROR : ZSB_DATA_ERROR, kInflateMsg[e]);
+            }
+            // drop this candidate: the piece continues into the next one
+        }
+        if (!any_bad) break;
+        cand.swap(kept);
+    }
+    uint64_t acc = 0;
+    if (total_bytes)
+        for (size_t i = 0; i < cand.size(); i++) *total_bytes += lens[i];
+    for (size_t i = 0; i < cand.size(); i++) {
+        if (lens[i] == 0 && acc == 0 && !ends.empty()) {   // Q10: a repeated marker belongs to the segment before it
+            ends.back() = cand[i];
+            continue;
+        }
+        acc += lens[i];
+        if (acc > seg_size) return fail(ctx, ZSB_DATA_ERROR, kInflateMsg[IE_SEG_SIZE]);
+        if (acc == seg_size) {
+            ends.push_back(cand[i]);
+            acc = 0;
+        }
+    }
+    if (acc) ends.push_back(cand.back());   // a short last segment
+    else if (ends.empty()) ends.push_back(cand.back());   // nothing but markers: one empty segment
+    return ZSB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char* zsb_version(void) { return "zsb200 0.1.0 sm_100a"; }
@@ -220,7 +324,7 @@ void zsb_ctx_destroy(zsb_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     DevBuf* bufs[] = {&ctx->in_stage, &ctx->out_stage, &ctx->sym, &ctx->blocks, &ctx->nblocks, &ctx->codes, &ctx->layout,
-                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status, &ctx->inf_scratch, &ctx->inf_carry};
+                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status, &ctx->inf_scratch, &ctx->inf_carry, &ctx->idx_cand};
     for (DevBuf* b : bufs) b->release();
     if (ctx->crc_tab) cudaFree(ctx->crc_tab);
     if (ctx->lz_stats) cudaFree(ctx->lz_stats);
@@ -437,8 +541,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     if (out_len) *out_len = 0;
     if (!in || (!out && out_cap)) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
     if (seg_size == 0 || seg_size > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "seg_size");
-    if (!seg_end_offsets) return fail(ctx, ZSB_STREAM_ERROR, "segment index scan is not implemented yet: pass seg_end_offsets");
-    if (nseg > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "too many segments");
+    if (seg_end_offsets && nseg > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "too many segments");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     timing_begin(ctx);
@@ -463,8 +566,18 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         if ((((unsigned)hdr[0] << 8) + hdr[1]) % 31 != 0) return fail(ctx, ZSB_DATA_ERROR, "incorrect header check");
         if (hdr[1] & 0x20) return fail(ctx, ZSB_NEED_DICT, "need dictionary");
     }
-    const uint64_t* d_seg_end = seg_end_offsets;
     std::vector<uint64_t> host_ends;
+    if (!seg_end_offsets) {
+        // no side-car: find the segments by their full-flush markers
+        if (n < (has_header ? 2u : 0u) + (has_trailer ? 6u : 0u)) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+        int rc = build_segment_index(ctx, d_in, n, has_header ? 2 : 0, n - (has_trailer ? 6 : 0), seg_size, host_ends);
+        if (rc != ZSB_OK) return rc;
+        seg_end_offsets = host_ends.data();
+        nseg = host_ends.size();
+        flags &= ~ZSB_OFFSETS_DEVICE;
+        if (nseg > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "too many segments");
+    }
+    const uint64_t* d_seg_end = seg_end_offsets;
     if (!(flags & ZSB_OFFSETS_DEVICE)) {
         CU(ctx->seg_end.reserve((nseg ? nseg : 1) * sizeof(uint64_t)));
         CU(cudaMemcpyAsync(ctx->seg_end.p, seg_end_offsets, nseg * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -573,6 +686,41 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         CU(cudaStreamSynchronize(st));
     }
     return has_trailer ? ZSB_STREAM_END : ZSB_OK;
+}
+
+int zsb_build_segment_index(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size, unsigned flags, uint64_t* seg_end_offsets,
+                            size_t cap, size_t* nseg, uint64_t* uncompressed_size)
+{
+    if (!ctx) return ZSB_STREAM_ERROR;
+    ctx->err.clear();
+    if (nseg) *nseg = 0;
+    if (uncompressed_size) *uncompressed_size = 0;
+    if (!in || !nseg) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
+    if (seg_size == 0 || seg_size > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "seg_size");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool has_header = !(flags & ZSB_NO_HEADER), has_trailer = !(flags & ZSB_NO_TRAILER);
+    if (n < (has_header ? 2u : 0u) + (has_trailer ? 6u : 0u)) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+    const uint8_t* d_in = reinterpret_cast<const uint8_t*>(in);
+    if (!(flags & ZSB_IN_DEVICE)) {
+        CU(ctx->in_stage.reserve(n ? n : 1));
+        CU(cudaMemcpyAsync(ctx->in_stage.p, in, n, cudaMemcpyHostToDevice, st));
+        d_in = ctx->in_stage.as<uint8_t>();
+    }
+    std::vector<uint64_t> ends;
+    uint64_t total = 0;
+    int rc = build_segment_index(ctx, d_in, n, has_header ? 2 : 0, n - (has_trailer ? 6 : 0), seg_size, ends, &total);
+    if (rc != ZSB_OK) return rc;
+    *nseg = ends.size();
+    if (uncompressed_size) *uncompressed_size = total;
+    if (seg_end_offsets) {
+        if (ends.size() > cap) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+        if (flags & ZSB_OFFSETS_DEVICE) {
+            CU(cudaMemcpyAsync(seg_end_offsets, ends.data(), ends.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        } else memcpy(seg_end_offsets, ends.data(), ends.size() * sizeof(uint64_t));
+    }
+    return ZSB_OK;
 }
 
 int zsb_adler32(zsb_ctx* ctx, uint32_t seed, const void* p, size_t n, unsigned flags, uint32_t* result)

@@ -5,14 +5,16 @@
 // (45 KiB) + the build scratch (2 KiB) => 4 CTAs per SM.
 #include "zsb_inflate_lanes.cuh"
 
+#include <cstdlib>
+
 namespace zsb {
 
 using namespace lanes;
 
 namespace {
 
-constexpr size_t kLaneSmem = 32 * sizeof(LaneTables) + sizeof(WarpScratch);
-static_assert((32 * sizeof(LaneTables)) % 8 == 0, "WarpScratch follows the tables and holds 64-bit words");
+static_assert(sizeof(LaneTables) % 4 == 0 && sizeof(WarpScratch) % 8 == 0, "shared-memory layout: scratch first, then the tables");
+size_t lane_smem(int segs_per_warp) { return sizeof(WarpScratch) + (size_t)segs_per_warp * sizeof(LaneTables); }
 
 __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 {
@@ -23,20 +25,23 @@ __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 
 }  // namespace
 
-__global__ void __launch_bounds__(32) inflate_lanes_kernel(InflateParams P, uint8_t* scratch)
+// segs_per_warp (S): lanes 0..S-1 decode a segment each, the others only help with the table builds.  Fewer segments
+// per warp = fewer divergent paths serialised per iteration and more warps for the same number of segments; the
+// launcher picks S from the number of segments so that the SMs have enough warps to hide latency.
+__global__ void __launch_bounds__(32) inflate_lanes_kernel(InflateParams P, uint8_t* scratch, int segs_per_warp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    LaneTables* tabs = reinterpret_cast<LaneTables*>(smem);
-    WarpScratch& sc = *reinterpret_cast<WarpScratch*>(smem + 32 * sizeof(LaneTables));
+    WarpScratch& sc = *reinterpret_cast<WarpScratch*>(smem);
+    LaneTables* tabs = reinterpret_cast<LaneTables*>(smem + sizeof(WarpScratch));
     const int lane = threadIdx.x;
     uint8_t* my_scratch = scratch + ((size_t)blockIdx.x * 32 + lane) * SCRATCH_STRIDE;
     uint8_t* glens = my_scratch;
     uint16_t* glong = reinterpret_cast<uint16_t*>(my_scratch + LENS_STRIDE);
-    LaneTables& T = tabs[lane];
+    LaneTables& T = tabs[lane < segs_per_warp ? lane : 0];
 
     Lane L;
     L.st = S_EXIT;
-    next_segment(L, P);
+    if (lane < segs_per_warp) next_segment(L, P);
 
     for (;;) {
         lane_step(L, T, glens, glong);
@@ -96,27 +101,80 @@ cudaError_t launch_inflate_carry_fixup(const InflateParams& P, cudaStream_t stre
     return cudaGetLastError();
 }
 
+// ---- segment index for streams without a side-car (mirrors InflateSync, Inflate.cs:386-448) --------------
+// Every full flush ends with an empty stored block whose LEN/NLEN bytes are 00 00 FF FF (Deflate.cs:710-712).  This kernel
+// lists the END offset of every occurrence; the host sorts them, has the pieces in between decoded in count-only mode and
+// merges pieces into segments (zsb_api.cu: build_segment_index).
+__global__ void __launch_bounds__(256) index_markers_kernel(const uint8_t* in, size_t begin, size_t end, uint64_t* cand,
+                                                            uint32_t cand_cap, uint32_t* ncand)
+{
+    // thread = one 4-byte aligned word and the 4 marker positions that start inside it
+    const uintptr_t base = reinterpret_cast<uintptr_t>(in) & ~(uintptr_t)3;
+    const size_t delta = reinterpret_cast<uintptr_t>(in) - base;       // in = base + delta
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(base);
+    const size_t w_first = (begin + delta) / 4, w_last = (end + delta + 3) / 4;   // words [w_first, w_last)
+    for (size_t w = w_first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < w_last; w += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t lo = __ldg(words + w);
+        const uint64_t hi = w + 1 < w_last ? __ldg(words + w + 1) : 0;
+        const uint64_t v = lo | (hi << 32);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((uint32_t)(v >> (8 * k)) != 0xFFFF0000u) continue;
+            const size_t p = w * 4 + k;               // offset from base
+            if (p < begin + delta || p + 4 > end + delta) continue;
+            const uint32_t slot = atomicAdd(ncand, 1u);
+            if (slot < cand_cap) cand[slot] = (uint64_t)(p - delta + 4);
+        }
+    }
+}
+
+cudaError_t launch_index_markers(const uint8_t* in, size_t begin, size_t end, uint64_t* cand, uint32_t cand_cap, uint32_t* ncand,
+                                 cudaStream_t stream)
+{
+    if (end < begin + 4) return cudaSuccess;
+    const size_t words = (end - begin) / 4 + 2;
+    size_t ctas = (words + 255) / 256;
+    if (ctas > 148 * 16) ctas = 148 * 16;
+    index_markers_kernel<<<(int)ctas, 256, 0, stream>>>(in, begin, end, cand, cand_cap, ncand);
+    return cudaGetLastError();
+}
+
 size_t inflate_lanes_scratch_bytes(int num_sms)
 {
-    return (size_t)num_sms * 8 * 32 * SCRATCH_STRIDE;   // up to 8 resident CTAs per SM
+    return (size_t)num_sms * 32 * 32 * SCRATCH_STRIDE;   // up to 32 resident CTAs per SM
 }
 
 cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     if (P.nseg == 0) return cudaSuccess;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLaneSmem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem(32));
         if (e != cudaSuccess) return e;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_lanes_kernel, 32, kLaneSmem) != cudaSuccess || per_sm < 1)
-            per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
+        attr_set = true;
     }
+    // Segments per warp: as many as still leave ~kWarpsWanted warps per SM (ZSB_INFLATE_SEGS_PER_WARP overrides).
+    static const int forced = [] {
+        const char* e = getenv("ZSB_INFLATE_SEGS_PER_WARP");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 32 ? v : 0;
+    }();
+    int S = forced;
+    if (!S) {
+        // measured on B200 (profiles/r01i_inflate_lanes_sweep.txt): with enough segments to keep every SM's resident
+        // warps full, 32 per warp is fastest (issue slots are shared 32 ways); below that, 6 per warp trades issue
+        // efficiency for more warps in flight
+        int full = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, inflate_lanes_kernel, 32, lane_smem(32)) != cudaSuccess || full < 1) full = 1;
+        S = (size_t)P.nseg * 4 >= (size_t)num_sms * full * 32 * 3 ? 32 : 6;
+    }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_lanes_kernel, 32, lane_smem(S)) != cudaSuccess || per_sm < 1) per_sm = 1;
     int ctas = num_sms * per_sm;
-    const int need = (int)((P.nseg + 31) / 32);
+    const int need = (int)((P.nseg + S - 1) / S);
     if (ctas > need) ctas = need;
     if ((size_t)ctas * 32 * SCRATCH_STRIDE > scratch_bytes) return cudaErrorInvalidValue;
-    inflate_lanes_kernel<<<ctas, 32, kLaneSmem, stream>>>(P, scratch);
+    inflate_lanes_kernel<<<ctas, 32, lane_smem(S), stream>>>(P, scratch, S);
     return cudaGetLastError();
 }
 

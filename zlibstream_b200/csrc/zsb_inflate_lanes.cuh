@@ -32,12 +32,15 @@ namespace lanes {
 #define ZL_HD __host__ __device__ __forceinline__
 
 #ifndef ZSB_LN_ROOT_L
-#define ZSB_LN_ROOT_L 9
+#define ZSB_LN_ROOT_L 8
 #endif
 constexpr int ROOT_L = ZSB_LN_ROOT_L;   // literal/length root table bits
 constexpr int ROOT_D = 6;               // distance root table bits
 constexpr int ROOT_BL = 7;              // bit-length code: always complete within the root (MAX_BL_BITS)
-constexpr int LONG_L = 96;              // long-code literal/length symbols kept in shared memory (the rest: global)
+#ifndef ZSB_LN_LONG_L
+#define ZSB_LN_LONG_L 96
+#endif
+constexpr int LONG_L = ZSB_LN_LONG_L;            // long-code literal/length symbols kept in shared memory (the rest: global)
 constexpr int LENS_STRIDE = 320;        // per-lane global scratch: code lengths of the block header (bytes)
 constexpr int GLONG_STRIDE = 288;       // per-lane global scratch: all long-code literal/length symbols (u16)
 constexpr int SCRATCH_STRIDE = LENS_STRIDE + 2 * GLONG_STRIDE;   // bytes per lane
@@ -84,6 +87,14 @@ struct Lane {
     uint32_t seg;
     int nl, nd, ci, prevlen, fixed;
     uint32_t stored_rem;
+    uint32_t cp_rem;       // bytes of the current symbol not yet appended (incl. the pending unit)
+    uint32_t pend_n;       // bytes of the pending unit, 0 = none
+    int pend_kind;         // UnitKind
+    uint32_t pend_val;     // U_LIT: the byte
+    uint32_t cp_D;         // U_MEM: distance
+    uint64_t plo, phi;     // U_PAT: 16 bytes of the periodic sequence
+    uint32_t ph, pd;       //        phase of the next unit, period
+    int count;             // count-only pass (segment index building): nothing is loaded from or stored to `out`
     uint32_t carry;        // Q14: leading bytes that repeat the previous segment's last byte (Rle streams only)
     uint64_t bl_lens;      // 19 x 3 bits
 };
@@ -183,6 +194,9 @@ ZL_HD void refill(Lane& L)
     const uint8_t* p = L.in + L.pos;
     if (((uintptr_t)p & 3u) == 0 && L.pos + 4 <= L.limit) {
         L.acc |= (uint64_t)ld_in_u32(p) << L.nbits;
+#ifdef __CUDA_ARCH__
+        if (((uintptr_t)p & 31u) == 0 && L.pos + 128 <= L.limit) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 96));   // the stream is read front to back
+#endif
         L.pos += 4;
         L.nbits += 32;
         return;
@@ -206,6 +220,7 @@ ZL_HD uint32_t byte_pos(const Lane& L) { return L.pos - (uint32_t)(L.nbits >> 3)
 // ---- output ----------------------------------------------------------------------------------------------------------
 ZL_HD void store_word(Lane& L, uint32_t vw, uint64_t w)
 {
+    if (L.count) return;
     if (vw >= L.sh) st_out_u64(L.ob8 + vw, w);
     else
         for (uint32_t k = L.sh - vw; k < 8; k++) st_out_u8(L.ob8 + vw + k, (uint8_t)(w >> (8 * k)));   // first word of an unaligned segment
@@ -234,6 +249,7 @@ ZL_HD void append_chunk(Lane& L, uint64_t val, uint32_t n)
 // makes the bytes of the partial word visible in memory (they stay in wbuf as well)
 ZL_HD void flush_partial(Lane& L)
 {
+    if (L.count) return;
     const uint32_t a = L.v & 7u, vw = L.v & ~7u;
     for (uint32_t k = 0; k < a; k++)
         if (vw + k >= L.sh) st_out_u8(L.ob8 + vw + k, (uint8_t)(L.wbuf >> (8 * k)));
@@ -248,37 +264,36 @@ ZL_HD uint64_t load_out8(const Lane& L, uint32_t sp, uint32_t n)
     return val;
 }
 
-// out[v + i] = out[v - d + i], i < len   (InfCodes.cs:243-283, InflateBlocks window copy)
-ZL_HD void copy_match(Lane& L, uint32_t len, uint32_t d)
+// ---- output units ----------------------------------------------------------------------------------------------------
+// Every symbol is emitted as "units" of at most 8 bytes, one unit per iteration of the lane (so a long match never makes
+// the other 31 lanes wait): a literal is a unit of one byte; a match is cut into 8-byte units that are
+//   U_MEM   read from the segment's earlier output (distance >= 9; below 15 the word under assembly is flushed first),
+//   U_PAT   generated from a 16-byte periodic extension of the last `d` bytes held in registers (distance <= 8: runs),
+//   U_ZERO  placeholders of a Q14 carried run.
+enum UnitKind { U_LIT = 0, U_MEM, U_PAT, U_ZERO };
+
+// Sets up U_PAT for a match of distance d <= 8 at the current position (InfCodes.cs:243-283 copies byte by byte).
+ZL_HD void pattern_setup(Lane& L, uint32_t d)
 {
-    uint32_t D = d, rem = len;
-    if (d < 15) {
-        // A run, or a source inside the word being assembled.  Emit whole periods from registers until the distance can
-        // be widened to a multiple of the period that is >= 15: from there the 8-byte loop only reads stored words.
-        flush_partial(L);
-        const uint32_t s = L.v - d, q = s & ~7u, b = s & 7u;
-        const uint64_t w0 = ld_out_u64(L.ob8 + q);
-        const uint64_t w1 = q + 8 < L.v ? ld_out_u64(L.ob8 + q + 8) : 0;
-        const uint64_t w2 = q + 16 < L.v ? ld_out_u64(L.ob8 + q + 16) : 0;
-        const uint64_t plo = b ? (w0 >> (8 * b)) | (w1 << (8 * (8 - b))) : w0;
-        const uint64_t phi = b ? (w1 >> (8 * b)) | (w2 << (8 * (8 - b))) : w1;
-        const uint32_t m = (14u + d) / d;
-        D = m * d;
-        uint32_t cnt = D - d;
-        if (cnt > len) cnt = len;
-        uint32_t kk = 0;
-        for (uint32_t k = 0; k < cnt; k++) {
-            const uint64_t src = kk < 8 ? plo >> (8 * kk) : phi >> (8 * (kk - 8));
-            append_byte(L, (uint32_t)src & 0xffu);
-            if (++kk == d) kk = 0;
-        }
-        rem -= cnt;
+    L.ph = 0;
+    L.pd = d;
+    if (L.count) return;
+    flush_partial(L);
+    const uint32_t s = L.v - d, q = s & ~7u, b = s & 7u;
+    uint64_t lo = ld_out_u64(L.ob8 + q) >> (8 * b);
+    if (b + d > 8) lo |= ld_out_u64(L.ob8 + q + 8) << (8 * (8 - b));
+    if (d < 8) lo &= (1ull << (8 * d)) - 1ull;
+    uint64_t hi = 0;
+    for (uint32_t f = d; f < 16; f *= 2) {   // (lo, hi) |= (lo, hi) << 8f
+        if (f < 8) {
+            hi |= (hi << (8 * f)) | (lo >> (64 - 8 * f));
+            lo |= lo << (8 * f);
+        } else hi |= lo << (8 * (f - 8));
     }
-    while (rem) {
-        const uint32_t n = rem < 8 ? rem : 8;
-        append_chunk(L, load_out8(L, L.v - D, n), n);
-        rem -= n;
-    }
+    L.plo = lo;
+    L.phi = hi;
+    L.ph = 0;
+    L.pd = d;
 }
 
 // ---- steps -----------------------------------------------------------------------------------------------------------
@@ -367,9 +382,12 @@ ZL_HD void stored_step(Lane& L)
         const uint8_t* p = L.in + L.pos;
         const uint32_t b = (uint32_t)((uintptr_t)p & 7u);
         const uint8_t* q = p - b;
-        uint64_t val = ld_in_u64(q) >> (8 * b);
-        if (b + n > 8) val |= ld_in_u64(q + 8) << (8 * (8 - b));
-        if (n < 8) val &= (1ull << (8 * n)) - 1ull;
+        uint64_t val = 0;
+        if (!L.count) {
+            val = ld_in_u64(q) >> (8 * b);
+            if (b + n > 8) val |= ld_in_u64(q + 8) << (8 * (8 - b));
+            if (n < 8) val &= (1ull << (8 * n)) - 1ull;
+        }
         append_chunk(L, val, n);
         L.pos += n;
         L.stored_rem -= n;
@@ -417,62 +435,119 @@ ZL_HD uint32_t long_code(const uint32_t* meta, uint64_t acc)
     return 0;
 }
 
-// One literal/length symbol, with its distance and copy if it is a match (InfCodes.cs:106-369)
+// One iteration of the symbol loop (InfCodes.cs:106-369), software-pipelined so that the L2 round trip of a match copy
+// hides behind the decoding of the NEXT symbol:
+//   (a) issue the loads of the pending unit (its source address is known since the previous iteration),
+//   (b) if that unit completes its symbol, decode the next literal/length (+ distance) code -- bit work and shared-memory
+//       lookups only, nothing that depends on the output,
+//   (c) append the pending unit,
+//   (d) turn the decoded symbol into the next pending unit (checks against the output position happen here).
+// Nothing is pending across a block boundary: END_BLOCK leaves pend_n == 0.
 ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
 {
-    refill(L);
-    uint32_t e = T.root_l[L.acc & ((1u << ROOT_L) - 1u)];
-    int sym;
-    if (e) {
-        drop(L, (int)(e & 15u));
-        sym = (int)(e >> 4);
-    } else {
-        e = long_code<ROOT_L>(T.meta_l, L.acc);
-        if (!e) return lane_fail(L, L.nbits <= 0 ? IE_TRUNCATED : IE_BAD_LCODE);
-        drop(L, (int)(e & 15u));
-        const uint32_t idx = e >> 4;
-        sym = idx < (uint32_t)LONG_L ? T.long_l[idx] : ld_scratch_u16(glong + idx);
+    // (a)
+    uint64_t w0 = 0, w1 = 0;
+    const uint32_t pn = L.pend_n;
+    if (pn && L.pend_kind == U_MEM && !L.count) {
+        if (L.cp_D < 15) flush_partial(L);
+        const uint32_t sp = L.v - L.cp_D, q = sp & ~7u, b = sp & 7u;
+        w0 = ld_out_u64(L.ob8 + q);
+        if (b + pn > 8) w1 = ld_out_u64(L.ob8 + q + 8);
     }
+    // (b)
+    const bool dec = L.cp_rem == pn;
+    int sym = 0;
+    uint32_t len = 0, d = 0;
+    int derr = IE_OK;
+    if (dec) {
+        refill(L);
+        uint32_t e = T.root_l[L.acc & ((1u << ROOT_L) - 1u)];
+        if (e) {
+            drop(L, (int)(e & 15u));
+            sym = (int)(e >> 4);
+        } else {
+            e = long_code<ROOT_L>(T.meta_l, L.acc);
+            if (!e) derr = L.nbits <= 0 ? IE_TRUNCATED : IE_BAD_LCODE;
+            else {
+                drop(L, (int)(e & 15u));
+                const uint32_t idx = e >> 4;
+                sym = idx < (uint32_t)LONG_L ? T.long_l[idx] : ld_scratch_u16(glong + idx);
+            }
+        }
+        if (sym > 256 && derr == IE_OK) {
+            const int ls = sym - 257;
+            if (ls >= 29) derr = IE_BAD_LCODE;
+            else {
+                {   // Trees.cs:85-115 length code -> base + extra bits
+                    const int eb = (ls < 8 || ls == 28) ? 0 : (ls - 4) >> 2;
+                    const uint32_t base = ls < 8 ? 3u + (uint32_t)ls : ls == 28 ? 258u : 3u + ((4u + ((uint32_t)ls & 3u)) << eb);
+                    len = base + peek(L, eb);
+                    drop(L, eb);
+                }
+                refill(L);
+                e = T.root_d[L.acc & ((1u << ROOT_D) - 1u)];
+                int ds = 0;
+                if (e) {
+                    drop(L, (int)(e & 15u));
+                    ds = (int)(e >> 4);
+                } else {
+                    e = long_code<ROOT_D>(T.meta_d, L.acc);
+                    if (!e) derr = L.nbits <= 0 ? IE_TRUNCATED : IE_BAD_DCODE;
+                    else {
+                        drop(L, (int)(e & 15u));
+                        ds = T.long_d[(e >> 4) & 31u];
+                    }
+                }
+                if (ds >= 30 && derr == IE_OK) derr = IE_BAD_DCODE;
+                {   // Trees.cs:75-98
+                    const int eb = ds < 4 ? 0 : (ds >> 1) - 1;
+                    const uint32_t base = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << (eb & 15));
+                    d = base + peek(L, eb & 15);
+                    drop(L, eb & 15);
+                }
+            }
+        }
+        if (derr == IE_OK && L.nbits < 0 && sym != 256) derr = IE_TRUNCATED;   // END_BLOCK: block_step checks
+    }
+    // (c)
+    if (pn) {
+        uint64_t val;
+        const int kind = L.pend_kind;
+        if (kind == U_LIT) val = L.pend_val;
+        else if (kind == U_MEM) {
+            const uint32_t b = (L.v - L.cp_D) & 7u;
+            val = w0 >> (8 * b);
+            if (b + pn > 8) val |= w1 << (8 * (8 - b));
+        } else if (kind == U_PAT) {
+            const uint32_t ph = L.ph;
+            val = ph ? (L.plo >> (8 * ph)) | (L.phi << (8 * (8 - ph))) : L.plo;
+            uint32_t nx = ph + (8u % L.pd);   // the next unit starts 8 bytes further into the period
+            if (nx >= L.pd) nx -= L.pd;
+            L.ph = nx;
+        } else val = 0;
+        if (pn < 8) val &= (1ull << (8 * pn)) - 1ull;
+        append_chunk(L, val, pn);
+        L.cp_rem -= pn;
+    }
+    // (d)
+    if (!dec) {
+        L.pend_n = L.cp_rem < 8 ? L.cp_rem : 8;
+        return;
+    }
+    L.pend_n = 0;
+    if (derr != IE_OK) return lane_fail(L, derr);
     if (sym < 256) {
-        if (L.nbits < 0) return lane_fail(L, IE_TRUNCATED);
         if (L.v >= L.vcap) return lane_fail(L, IE_OUTPUT_OVERFLOW);
-        append_byte(L, (uint32_t)sym);
+        L.pend_kind = U_LIT;
+        L.pend_val = (uint32_t)sym;
+        L.pend_n = 1;
+        L.cp_rem = 1;
         return;
     }
     if (sym == 256) {
-        L.st = S_BLOCK;   // block_step checks nbits
+        L.st = S_BLOCK;
         return;
     }
-    const int ls = sym - 257;
-    if (ls >= 29) return lane_fail(L, IE_BAD_LCODE);
-    uint32_t len;
-    {   // Trees.cs:85-115 length code -> base + extra bits
-        const int eb = (ls < 8 || ls == 28) ? 0 : (ls - 4) >> 2;
-        const uint32_t base = ls < 8 ? 3u + (uint32_t)ls : ls == 28 ? 258u : 3u + ((4u + ((uint32_t)ls & 3u)) << eb);
-        len = base + peek(L, eb);
-        drop(L, eb);
-    }
-    refill(L);
-    e = T.root_d[L.acc & ((1u << ROOT_D) - 1u)];
-    int ds;
-    if (e) {
-        drop(L, (int)(e & 15u));
-        ds = (int)(e >> 4);
-    } else {
-        e = long_code<ROOT_D>(T.meta_d, L.acc);
-        if (!e) return lane_fail(L, L.nbits <= 0 ? IE_TRUNCATED : IE_BAD_DCODE);
-        drop(L, (int)(e & 15u));
-        ds = T.long_d[(e >> 4) & 31u];
-    }
-    if (ds >= 30) return lane_fail(L, IE_BAD_DCODE);
-    uint32_t d;
-    {   // Trees.cs:75-98
-        const int eb = ds < 4 ? 0 : (ds >> 1) - 1;
-        const uint32_t base = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << eb);
-        d = base + peek(L, eb);
-        drop(L, eb);
-    }
-    if (L.nbits < 0) return lane_fail(L, IE_TRUNCATED);
     if (L.v + len > L.vcap) return lane_fail(L, IE_OUTPUT_OVERFLOW);
     const uint32_t o = L.v - L.sh;
     if (d > o || o - d < L.carry) {
@@ -480,14 +555,16 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
         // Those bytes are placeholders here; inflate_carry_fixup_kernel fills them in once every segment is decoded.
         if (!(d == 1 && o == L.carry && L.seg > 0)) return lane_fail(L, IE_DIST_TOO_FAR);
         L.carry += len;
-        for (uint32_t rem = len; rem;) {
-            const uint32_t n = rem < 8 ? rem : 8;
-            append_chunk(L, 0, n);
-            rem -= n;
-        }
-        return;
+        L.pend_kind = U_ZERO;
+    } else if (d <= 8) {
+        pattern_setup(L, d);
+        L.pend_kind = U_PAT;
+    } else {
+        L.cp_D = d;
+        L.pend_kind = U_MEM;
     }
-    copy_match(L, len, d);
+    L.cp_rem = len;
+    L.pend_n = len < 8 ? len : 8;
 }
 
 // Start of a segment: a full-flush segment begins byte aligned with an empty history (Deflate.cs:596-605).
@@ -505,13 +582,20 @@ ZL_HD void begin_segment(Lane& L, const InflateParams& P, uint32_t seg)
     L.fixed = 0;
     L.nl = L.nd = L.ci = L.prevlen = 0;
     L.stored_rem = 0;
+    L.cp_rem = L.pend_n = 0;
+    L.pend_kind = U_LIT;
+    L.pend_val = L.cp_D = L.ph = 0;
+    L.pd = 1;
+    L.plo = L.phi = 0;
     L.carry = 0;
     L.bl_lens = 0;
     const uint64_t c_begin = seg == 0 ? P.first_offset : P.seg_end[seg - 1];
     const uint64_t c_end = P.seg_end[seg];
-    const uint64_t o_begin = (uint64_t)seg * P.seg_size;
+    L.count = P.count_only;
+    const uint64_t o_begin = P.count_only ? 0 : (uint64_t)seg * P.seg_size;
     uint64_t room = o_begin < P.out_cap ? P.out_cap - o_begin : 0;
     if (room > P.seg_size) room = P.seg_size;
+    if (P.count_only) room = 0xE0000000u;   // pieces between candidate markers: any length
     uint8_t* ob = P.out + o_begin;
     L.sh = (uint32_t)((uintptr_t)ob & 7u);
     L.ob8 = ob - L.sh;
@@ -534,7 +618,7 @@ ZL_HD void finish_segment(Lane& L, const InflateParams& P)
     flush_partial(L);
     const uint32_t o = L.v - L.sh;
     // every segment but the last holds exactly seg_size bytes (that is what places the output)
-    if (L.err == IE_OK && L.seg + 1 < P.nseg && o != P.seg_size) L.err = IE_SEG_SIZE;
+    if (L.err == IE_OK && !L.count && L.seg + 1 < P.nseg && o != P.seg_size) L.err = IE_SEG_SIZE;
     P.seg_out_len[L.seg] = o;
     P.seg_status[L.seg] = L.err;
     if (P.seg_carry) P.seg_carry[L.seg] = L.carry;
@@ -555,7 +639,10 @@ ZL_HD bool carry_fill_value(const InflateParams& P, uint32_t k, uint8_t& val)
     return false;
 }
 
-constexpr int SYMS_PER_STEP = 4;
+#ifndef ZSB_LN_SYMS_PER_STEP
+#define ZSB_LN_SYMS_PER_STEP 4
+#endif
+constexpr int SYMS_PER_STEP = ZSB_LN_SYMS_PER_STEP;
 
 // One bounded unit of work in whatever state the lane is in (S_BUILD_* and S_FINISH are the caller's).
 ZL_HD void lane_step(Lane& L, const LaneTables& T, uint8_t* glens, const uint16_t* glong)

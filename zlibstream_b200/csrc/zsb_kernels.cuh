@@ -96,6 +96,7 @@ struct InflateParams {
     unsigned int* work_counter;
     uint32_t* seg_carry = nullptr;   // [nseg] Q14: leading bytes that repeat the previous segment's last byte (lane kernel)
     unsigned int* carry_flag = nullptr;   // set to 1 if any seg_carry is non-zero
+    int count_only = 0;              // lane kernel: decode lengths and status only (segment index building)
 };
 cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream);
 // Lane-per-segment kernel (zsb_inflate_lanes.cu): the default.  scratch: inflate_lanes_scratch_bytes(num_sms) bytes.
@@ -103,9 +104,9 @@ size_t inflate_lanes_scratch_bytes(int num_sms);
 cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream);
 // Q14 fix-up after the lane kernel: fills the carried leading bytes of Rle segments.
 cudaError_t launch_inflate_carry_fixup(const InflateParams& P, cudaStream_t stream);
-// Scans `in` for full-flush markers and validates them into a segment index (device side).
-cudaError_t launch_index_markers(const uint8_t* in, size_t n, uint64_t first_offset, uint64_t* cand, uint32_t cand_cap,
-                                 uint32_t* ncand, cudaStream_t stream);
+// Lists the end offset of every 00 00 FF FF inside in[begin, end) (unordered; *ncand may exceed cand_cap).
+cudaError_t launch_index_markers(const uint8_t* in, size_t begin, size_t end, uint64_t* cand, uint32_t cand_cap, uint32_t* ncand,
+                                 cudaStream_t stream);
 
 enum InflateErr {
     IE_OK = 0, IE_BLOCK_TYPE, IE_STORED_LEN, IE_TOO_MANY_SYMS, IE_BAD_REPEAT, IE_OVERSUB_BL, IE_INCOMPLETE_BL,

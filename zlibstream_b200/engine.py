@@ -129,6 +129,22 @@ class Engine:
         del keep
         return out.raw[:out_len.value], adler.value
 
+    def build_segment_index(self, comp, seg_size: int, header: bool = True, trailer: bool = True):
+        """Segment index of a full-flush-segmented stream without a side-car (zsb_build_segment_index).
+        Returns ([segment end offsets], uncompressed size)."""
+        addr, n, keep = _addr(comp)
+        flags = (0 if header else _native.ZSB_NO_HEADER) | (0 if trailer else _native.ZSB_NO_TRAILER)
+        nseg = ctypes.c_size_t(0)
+        total = ctypes.c_uint64(0)
+        rc = self._lib.zsb_build_segment_index(self._h, addr, n, seg_size, flags, None, 0, ctypes.byref(nseg), ctypes.byref(total))
+        self._check(rc, False)
+        ends = (ctypes.c_uint64 * max(nseg.value, 1))()
+        rc = self._lib.zsb_build_segment_index(self._h, addr, n, seg_size, flags, ends, nseg.value, ctypes.byref(nseg),
+                                               ctypes.byref(total))
+        self._check(rc, False)
+        del keep
+        return list(ends)[:nseg.value], total.value
+
     def adler32(self, data, seed: int = 1) -> int:
         addr, n, keep = _addr(data)
         res = ctypes.c_uint32(0)

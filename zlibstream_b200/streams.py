@@ -247,7 +247,10 @@ class ZlibInputStream(io.RawIOBase):
         comp = self.BaseStream.read()
         self._total_in = len(comp)
         if self._ends is None:
-            raise ZlibStreamException("inflating: segment end offsets are required until the device marker scan lands")
+            # a stream written by the reference carries no side-car: find the segments by their full-flush markers
+            self._ends, total = self._engine.build_segment_index(comp, self._seg_size)
+            if self._usize is None:
+                self._usize = total
         nseg = len(self._ends)
         cap = self._usize if self._usize is not None else nseg * self._seg_size
         self._decoded, self.Adler = self._engine.inflate_segments(comp, self._ends, self._seg_size, cap)

@@ -182,10 +182,11 @@ size_t env_size(const char* name, size_t dflt)
 namespace {
 
 // Segment index of a stream that comes without a side-car (the reference's own resynchronisation is
-// InflateSync, Inflate.cs:386-448).  Candidates = every 00 00 FF FF in the body; the pieces between consecutive candidates
-// are decoded in count-only mode; a piece that does not decode is a chance occurrence of the pattern (inside a stored
-// block or inside Huffman data) and is merged with its successor; pieces are then grouped into segments of seg_size
-// bytes -- zero-length pieces (the repeated markers of Q10) stay with the segment they follow.
+// InflateSync, Inflate.cs:386-448).  Every 00 00 FF FF in the body is a candidate segment START (the byte after it); all
+// candidates are decoded side by side in count-only mode, each until the first empty stored block it meets, which gives
+// the piece's true end.  Following those ends from the first byte of the body visits exactly the real flush points --
+// chance occurrences of the pattern (inside stored or Huffman data) are never reached.  Pieces are then grouped into
+// segments of seg_size bytes; zero-length pieces (the repeated markers of Q10) stay with the segment they follow.
 int build_segment_index(zsb_ctx* ctx, const uint8_t* d_in, size_t n, uint64_t first, uint64_t body_end, size_t seg_size,
                         std::vector<uint64_t>& ends, uint64_t* total_bytes = nullptr)
 {
@@ -210,73 +211,70 @@ int build_segment_index(zsb_ctx* ctx, const uint8_t* d_in, size_t n, uint64_t fi
     CU(cudaStreamSynchronize(st));
     std::sort(cand.begin(), cand.end());
     if (cand.empty() || cand.back() != body_end) return fail(ctx, ZSB_DATA_ERROR, "stream does not end with a full-flush marker");
+    const size_t np = cand.size();   // piece k starts at cand[k-1] (k = 0: first); nothing starts at cand[np-1] = body_end
     CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
-    std::vector<int> status;
-    std::vector<uint32_t> lens;
-    for (int pass = 0;; pass++) {
-        const size_t np = cand.size();
-        CU(ctx->seg_end.reserve(np * sizeof(uint64_t)));
-        CU(ctx->inf_len.reserve(np * sizeof(uint32_t)));
-        CU(ctx->inf_status.reserve(np * sizeof(int)));
-        CU(cudaMemcpyAsync(ctx->seg_end.p, cand.data(), np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-        InflateParams I;
-        I.in = d_in;
-        I.n = n;
-        I.seg_end = ctx->seg_end.as<uint64_t>();
-        I.first_offset = first;
-        I.nseg = (uint32_t)np;
-        I.seg_size = 0;
-        I.out = nullptr;
-        I.out_cap = 0;
-        I.seg_out_len = ctx->inf_len.as<uint32_t>();
-        I.seg_adler = nullptr;
-        I.seg_status = ctx->inf_status.as<int>();
-        I.work_counter = d_work;
-        I.count_only = 1;
-        CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
-        ctx->launches++;
-        status.resize(np);
-        lens.resize(np);
-        CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, np * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        std::vector<uint64_t> kept;
-        kept.reserve(np);
-        bool any_bad = false;
-        for (size_t i = 0; i < np; i++) {
-            if (status[i] == IE_OK) {
-                kept.push_back(cand[i]);
-                continue;
+    CU(ctx->seg_end.reserve(np * sizeof(uint64_t)));
+    CU(ctx->inf_len.reserve(np * sizeof(uint32_t)));
+    CU(ctx->inf_status.reserve(np * sizeof(int)));
+    CU(ctx->idx_cand.reserve(np * sizeof(uint64_t)));
+    CU(cudaMemcpyAsync(ctx->seg_end.p, cand.data(), np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    InflateParams I;
+    I.in = d_in;
+    I.n = n;
+    I.seg_end = ctx->seg_end.as<uint64_t>();
+    I.first_offset = first;
+    I.nseg = (uint32_t)np;
+    I.seg_size = (uint32_t)seg_size;
+    I.out = nullptr;
+    I.out_cap = 0;
+    I.seg_out_len = ctx->inf_len.as<uint32_t>();
+    I.seg_adler = nullptr;
+    I.seg_status = ctx->inf_status.as<int>();
+    I.work_counter = d_work;
+    I.count_only = 1;
+    I.count_body_end = body_end;
+    I.seg_found_end = ctx->idx_cand.as<uint64_t>();   // the unsorted candidate list is no longer needed
+    CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+    ctx->launches++;
+    std::vector<int> status(np);
+    std::vector<uint32_t> lens(np);
+    std::vector<uint64_t> found(np);
+    CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, np * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(found.data(), ctx->idx_cand.p, np * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t pos = first, acc = 0;
+    while (pos < body_end) {
+        size_t k = 0;
+        if (pos != first) {
+            auto it = std::lower_bound(cand.begin(), cand.end(), pos);
+            if (it == cand.end() || *it != pos) return fail(ctx, ZSB_DATA_ERROR, "invalid stored block lengths");
+            k = (size_t)(it - cand.begin()) + 1;
+        }
+        if (k >= np) return fail(ctx, ZSB_DATA_ERROR, "invalid stored block lengths");
+        if (status[k] != IE_OK) {
+            int e = status[k];
+            if (e < 0 || e > IE_SEG_SIZE) e = IE_TRUNCATED;
+            if (e == IE_OUTPUT_OVERFLOW) e = IE_SEG_SIZE;   // more than seg_size bytes before the next flush point
+            return fail(ctx, e == IE_TRUNCATED ? ZSB_BUF_ERROR : ZSB_DATA_ERROR, kInflateMsg[e]);
+        }
+        const uint64_t e = found[k];
+        if (e <= pos || e > body_end) return fail(ctx, ZSB_DATA_ERROR, "invalid stored block lengths");
+        if (total_bytes) *total_bytes += lens[k];
+        if (lens[k] == 0 && acc == 0 && !ends.empty()) ends.back() = e;   // Q10: a repeated marker belongs to the segment before it
+        else {
+            acc += lens[k];
+            if (acc > seg_size) return fail(ctx, ZSB_DATA_ERROR, kInflateMsg[IE_SEG_SIZE]);
+            if (acc == seg_size) {
+                ends.push_back(e);
+                acc = 0;
             }
-            any_bad = true;
-            if (i + 1 == np || pass >= 8) {   // nothing left to merge with: the data really is damaged
-                int e = status[i];
-                if (e < 0 || e > IE_SEG_SIZE) e = IE_TRUNCATED;
-                return fail(ctx, (e == IE_TRUNCATED || e == IE_OUTPUT_OVERFLOW) ? ZSB_BUF_ERROR : ZSB_DATA_ERROR, kInflateMsg[e]);
-            }
-            // drop this candidate: the piece continues into the next one
         }
-        if (!any_bad) break;
-        cand.swap(kept);
+        pos = e;
     }
-    uint64_t acc = 0;
-    if (total_bytes)
-        for (size_t i = 0; i < cand.size(); i++) *total_bytes += lens[i];
-    for (size_t i = 0; i < cand.size(); i++) {
-        if (lens[i] == 0 && acc == 0 && !ends.empty()) {   // Q10: a repeated marker belongs to the segment before it
-            ends.back() = cand[i];
-            continue;
-        }
-        acc += lens[i];
-        if (acc > seg_size) return fail(ctx, ZSB_DATA_ERROR, kInflateMsg[IE_SEG_SIZE]);
-        if (acc == seg_size) {
-            ends.push_back(cand[i]);
-            acc = 0;
-        }
-    }
-    if (acc) ends.push_back(cand.back());   // a short last segment
-    else if (ends.empty()) ends.push_back(cand.back());   // nothing but markers: one empty segment
+    if (acc) ends.push_back(body_end);                     // a short last segment
+    else if (ends.empty()) ends.push_back(body_end);       // nothing but markers: one empty segment
     return ZSB_OK;
 }
 

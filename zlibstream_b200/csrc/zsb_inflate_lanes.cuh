@@ -95,6 +95,7 @@ struct Lane {
     uint64_t plo, phi;     // U_PAT: 16 bytes of the periodic sequence
     uint32_t ph, pd;       //        phase of the next unit, period
     int count;             // count-only pass (segment index building): nothing is loaded from or stored to `out`
+    uint32_t found;        // count-only: offset just past the full-flush marker that ended the piece, 0 = none yet
     uint32_t carry;        // Q14: leading bytes that repeat the previous segment's last byte (Rle streams only)
     uint64_t bl_lens;      // 19 x 3 bits
 };
@@ -318,6 +319,7 @@ ZL_HD void block_step(Lane& L)
     const uint32_t used = byte_pos(L);
     if (L.nbits < 0 || used > L.end) return lane_fail(L, IE_TRUNCATED);   // ran past the segment's bytes
     if (used == L.end) {                                                  // clean end, after the byte-aligned full-flush marker
+        if (L.count) return lane_fail(L, IE_TRUNCATED);                   // a piece ends AT a marker, not at the end of the data
         L.st = S_FINISH;
         return;
     }
@@ -343,6 +345,10 @@ ZL_HD void block_step(Lane& L)
         L.nbits = 0;
         L.stored_rem = l;
         L.st = l ? S_STORED : S_BLOCK;
+        if (L.count && l == 0) {   // the marker that ends every full flush
+            L.found = src;
+            L.st = S_FINISH;
+        }
     } else if (type == 1) {
         if (peek(L, 7) == 0) {   // the empty static block of every flush: END_BLOCK is seven zero bits
             drop(L, 7);
@@ -590,12 +596,12 @@ ZL_HD void begin_segment(Lane& L, const InflateParams& P, uint32_t seg)
     L.carry = 0;
     L.bl_lens = 0;
     const uint64_t c_begin = seg == 0 ? P.first_offset : P.seg_end[seg - 1];
-    const uint64_t c_end = P.seg_end[seg];
+    const uint64_t c_end = P.count_only ? P.count_body_end : P.seg_end[seg];
     L.count = P.count_only;
+    L.found = 0;
     const uint64_t o_begin = P.count_only ? 0 : (uint64_t)seg * P.seg_size;
     uint64_t room = o_begin < P.out_cap ? P.out_cap - o_begin : 0;
-    if (room > P.seg_size) room = P.seg_size;
-    if (P.count_only) room = 0xE0000000u;   // pieces between candidate markers: any length
+    if (room > P.seg_size || P.count_only) room = P.seg_size;
     uint8_t* ob = P.out + o_begin;
     L.sh = (uint32_t)((uintptr_t)ob & 7u);
     L.ob8 = ob - L.sh;
@@ -621,6 +627,7 @@ ZL_HD void finish_segment(Lane& L, const InflateParams& P)
     if (L.err == IE_OK && !L.count && L.seg + 1 < P.nseg && o != P.seg_size) L.err = IE_SEG_SIZE;
     P.seg_out_len[L.seg] = o;
     P.seg_status[L.seg] = L.err;
+    if (P.seg_found_end) P.seg_found_end[L.seg] = L.found ? (uint64_t)(L.in - P.in) + L.found : 0;
     if (P.seg_carry) P.seg_carry[L.seg] = L.carry;
     if (L.carry && P.carry_flag) *P.carry_flag = 1;
 }

@@ -96,7 +96,13 @@ struct InflateParams {
     unsigned int* work_counter;
     uint32_t* seg_carry = nullptr;   // [nseg] Q14: leading bytes that repeat the previous segment's last byte (lane kernel)
     unsigned int* carry_flag = nullptr;   // set to 1 if any seg_carry is non-zero
-    int count_only = 0;              // lane kernel: decode lengths and status only (segment index building)
+    // lane kernel, segment index building: count_only decodes lengths and status only; piece k starts at
+    // seg_end[k-1] (first_offset for k = 0) and runs to the first empty stored block (the full-flush marker,
+    // Deflate.cs:710-712), whose end offset goes to seg_found_end[k]; it may read up to count_body_end and produce at
+    // most seg_size bytes
+    int count_only = 0;
+    uint64_t count_body_end = 0;
+    uint64_t* seg_found_end = nullptr;
 };
 cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream);
 // Lane-per-segment kernel (zsb_inflate_lanes.cu): the default.  scratch: inflate_lanes_scratch_bytes(num_sms) bytes.

@@ -42,11 +42,9 @@ struct Smem {
     uint32_t* batch_seq;
     uint16_t* tile_hh;   // TILE_MAX: what InsertString returned for each position of the current DeflateSlow tile
     uint2* tile_rec;     // TILE_MAX: Longest_match results of the tile (full / quarter chain budget)
-    uint32_t* slot2;      // SLOT2_COUNT: second-chance arbitration for lanes that lost a slot to a different hash
-    uint32_t* fast_masks; // FM_KINDS * FAST_WARPS ballots of the DeflateFast batch
-    uint16_t* fast_endl;  // FAST_NB: where the parse stands after each batch position if it is a parse point
-    uint16_t* fast_mst;   // FAST_NB: match start of each batch position
-    uint2* fast_fn;       // FAST_NB: (first stop | next << 16) at or after each position, and the same one hop further
+    uint32_t* fast_masks; // 2 * 8 ballots of the DeflateFast batch (per warp)
+    uint16_t* fast_endl;  // 64: next parse point of each batch position if it is one
+    uint16_t* fast_mst;   // 64: match start of each batch position
 };
 
 __device__ __forceinline__ uint32_t hash_of(const Smem& sm, uint32_t v, int hash_variant)
@@ -251,44 +249,20 @@ __device__ __forceinline__ int warp_extend_match(const uint8_t* win, int p, int 
     return len < MAX_MATCH ? len : MAX_MATCH;
 }
 
-// DeflateFast (Deflate.Fast.cs:20-128) by FAST_WARPS warps: FAST_NB consecutive positions are evaluated speculatively
-// as parse points (thread i = str_start + i) against the hash table as it stands before the batch.
-//
-//   spec     every lane hashes its position, fetches head[h] and (level 1) all <= 4 chain links, and compares the four
-//            candidate strings 16 bytes at a time side by side; the selection visits them in Longest_match's order
-//            (Deflate.cs:1022-1100).  A 16-byte tie is extended by the lane itself up to 64 bytes; beyond that the lane is
-//            marked X and the exact length is found by a whole warp, only if the lane turns out to be a parse point.
-//   clean    a lane may trust its speculation only if no earlier lane of the batch has its hash (the chain would start
-//            inside the batch).  Arbitration is a slot table: atomicMax of (batch seq | inverted lane | hash); the winner
-//            of a slot is its first lane.  A lane that lost to a DIFFERENT hash (false sharing, ~idx/4096 per lane)
-//            retries in a second, smaller table; winning there is proof too, because every earlier lane of its own hash
-//            lost the same primary slot to the same winner.  Everything else is "dirty", and so is a lane the Q3
-//            pre-insert touched (head[h] >= position).
-//   links    stops = match lanes | dirty lanes.  Every lane i publishes (first stop n at or after i, where the parse
-//            stands after taking n), then the same pair one hop further on, so the greedy walk below advances TWO
-//            matches per dependent shared-memory load instead of one per ballot/ffs/shift chain.
-//   walk     uniform, every warp on its own: follows the links, collecting the taken matches in a bit set; an X lane is
-//            extended in place; a dirty lane ends the round.
-//   classify every lane finds the last taken match below it: covered (not a parse point; inserted iff the match is
-//            <= max_lazy long, Deflate.Fast.cs:81-104) or a parse point (literal or taken match).  Symbols are stored in
-//            position order; clean inserted lanes commit InsertString side by side (their hashes are pairwise distinct),
-//            dirty inserted lanes follow one at a time.
-//   dirty    the reference iteration is executed literally for that one position (fast_step); the walk then RESUMES in
-//            the same batch: the speculation of every later clean lane is still exact, since nothing inserted before it
-//            in this batch has its hash.
+// DeflateFast (Deflate.Fast.cs:20-128) by FAST_WARPS warps: FAST_WARPS * 32 consecutive positions are evaluated
+// speculatively as parse points (thread i = str_start + i) against the hash table as it stands before the batch; a
+// mask walk then resolves the greedy parse, and the inserts of the positions the reference would have inserted are
+// committed in position order.  A position whose hash also occurs earlier in the same batch cannot be speculated on
+// (its chain would start inside the batch): when the parse reaches one, the batch ends there and the next one starts
+// at it.  A position the Q3 pre-insert touched (head[h] >= position) runs the reference iteration literally.
+// "Occurs earlier in the batch" is decided through a small slot table (atomicMax of a batch-sequence | index key per
+// hash slot; __match_any_sync costs ~12 cycles per distinct value on sm_100, 385 cycles for 32 hashes): a thread is
+// clean iff it is the first of the batch in its slot, which errs only towards "not clean".
+// The warps exchange six ballots and one u16 per position through shared memory and each of them runs the (uniform)
+// walk on its own, so three CTA-partial barriers per batch are all the synchronisation there is.
 // Runs until the window needs refilling / sliding or the segment is done.
-#ifndef ZSB_FAST_WARPS
-#define ZSB_FAST_WARPS 4
-#endif
-constexpr int FAST_WARPS = ZSB_FAST_WARPS;
+constexpr int FAST_WARPS = 2;
 constexpr int FAST_NB = FAST_WARPS * 32;
-constexpr int FAST_IDX_BITS = FAST_WARPS <= 1 ? 5 : FAST_WARPS <= 2 ? 6 : FAST_WARPS <= 4 ? 7 : 8;
-constexpr uint32_t FAST_SEQ_MAX = (1u << (32 - 15 - FAST_IDX_BITS)) - 1u;
-constexpr int SLOT2_COUNT = 1024;
-constexpr uint32_t SLOT2_MASK = SLOT2_COUNT - 1;
-constexpr uint32_t FN_NONE = 0xFFFFu, FN_SPECIAL = 0xFFFEu;
-enum { FM_STOP = 0, FM_SPECIAL, FM_X, FM_SHORT, FM_PM, FM_SER, FM_KINDS };
-static_assert(FAST_NB <= 256 && FAST_NB < MIN_LOOKAHEAD, "a batch must not outrun the prev[] slots its searches read");
 
 __device__ __forceinline__ void fast_bar()
 {
@@ -299,14 +273,11 @@ __device__ __forceinline__ void fast_bar()
 __device__ void parse_fast_multi(const Smem& sm, ParserState& s, ParserState* shared_state, const SegOut& o,
                                  const LevelCfg& cfg, int strategy, int hash_variant, unsigned long long* stats)
 {
-    constexpr int W = FAST_WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, idx = threadIdx.x;   // idx < FAST_NB
-    const uint32_t lane_lt = (1u << lane) - 1u;
+    const uint64_t below = (1ull << idx) - 1ull;
     const bool quick = cfg.chain <= 4 && cfg.nice <= 16;  // level 1: the whole chain is probed in one round of loads
-    const bool search = strategy != 2;   // HuffmanOnly never searches (Deflate.Fast.cs:64): its hash table cannot reach the output
-    long long st_t0 = 0, st_t1 = 0, st_t2 = 0;
+    long long st_t0 = 0, st_t1 = 0, st_t2 = 0, st_t3 = 0;
     uint32_t seq = *sm.batch_seq;
-    uint32_t* const masks = sm.fast_masks;
     for (;;) {
         if (s.lookahead < MIN_LOOKAHEAD) {
             if (fill_needed(s)) break;
@@ -324,34 +295,32 @@ __device__ void parse_fast_multi(const Smem& sm, ParserState& s, ParserState* sh
         }
         if (nact > FAST_NB) nact = FAST_NB;
         if (nact > BLOCK_SYMS - s.last_lit) nact = BLOCK_SYMS - s.last_lit;
+        const uint64_t act = nact >= 64 ? ~0ull : (1ull << nact) - 1ull;
 
         const int S = s.str_start, LA = s.lookahead;
         const int p = S + idx, la = LA - idx;
         if (stats) st_t0 = clock64();
-        // ---- spec ----
-        if (seq >= FAST_SEQ_MAX) {   // the sequence field of the slot keys wraps: start over with empty tables
-            for (int i = idx; i < SLOT_COUNT; i += FAST_NB) sm.slot[i] = 0;
-            for (int i = idx; i < SLOT2_COUNT; i += FAST_NB) sm.slot2[i] = 0;
-            seq = 0;
-            fast_bar();
-        }
-        seq++;
-        const bool hashed = search && la >= MIN_MATCH;
-        uint32_t h = 0, key = 0;
+        // ---- speculative phase ----
+        const bool hashed = la >= MIN_MATCH;
+        uint32_t h = 0;
         int c0 = 0;
         uint32_t scan[4];
         lds16_unaligned(sm.win, p, scan);
+        bool first_in_slot = true;
+        seq++;
+        const uint32_t key = (seq << 6) | (uint32_t)(63 - idx);
         if (hashed) {
             h = hash_of(sm, __funnelshift_r(scan[0], scan[1], 16), hash_variant);
-            key = (seq << (15 + FAST_IDX_BITS)) | ((uint32_t)(FAST_NB - 1 - idx) << 15) | h;
             atomicMax(&sm.slot[h & SLOT_MASK], key);
             c0 = sm.head[h];
         }
-        const bool hard = hashed && c0 >= p;   // Q2/Q3: the refill pre-inserted this position (or the next)
-        const bool cand = hashed && !hard && idx < nact && c0 != 0 && p - c0 <= MAX_DIST;
+        fast_bar();
+        if (hashed) first_in_slot = sm.slot[h & SLOT_MASK] == key;
+        const bool hard = hashed && c0 >= p;                 // Q2/Q3: the refill pre-inserted this position (or the next)
+        const bool dirty = hashed && (!first_in_slot || hard);
         int best = MIN_MATCH - 1, mstart = 0;
-        bool ext = false;   // best == 16 stands for "at least 16"
-        if (cand) {
+        bool ext = false;  // best == 16 stands for "at least 16": the exact length is found if the position is a parse point
+        if (hashed && !dirty && idx < nact && c0 != 0 && p - c0 <= MAX_DIST && strategy != 2) {
             const int nice = cfg.nice < la ? cfg.nice : la;
             const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
             if (quick) {
@@ -366,8 +335,8 @@ __device__ void parse_fast_multi(const Smem& sm, ParserState& s, ParserState* sh
                 lds16_unaligned(sm.win, c2, w2);
                 lds16_unaligned(sm.win, c3, w3);
                 const int L0 = prefix16(scan, w0), L1 = prefix16(scan, w1), L2 = prefix16(scan, w2), L3 = prefix16(scan, w3);
-                bool go = true;
-                if (L0 > best) { best = L0; mstart = c0; if (L0 >= nice) go = false; }
+                bool go = c0 < p;
+                if (go && L0 > best) { best = L0; mstart = c0; if (L0 >= nice) go = false; }
                 go = go && c1 > limit && cfg.chain > 1 && c1 < p;
                 if (go && L1 > best) { best = L1; mstart = c1; if (L1 >= nice) go = false; }
                 go = go && c2 > limit && cfg.chain > 2 && c2 < p;
@@ -397,221 +366,138 @@ __device__ void parse_fast_multi(const Smem& sm, ParserState& s, ParserState* sh
                 } while (cur > limit && --chain != 0);
             }
         }
-        fast_bar();
-        // ---- clean? ----
-        bool clean = false, retry = false;
-        if (hashed) {
-            const uint32_t k = sm.slot[h & SLOT_MASK];
-            if (k == key) clean = true;
-            else if ((k & HASH_MASK) != h) {
-                retry = true;
-                atomicMax(&sm.slot2[(h >> 5) & SLOT2_MASK], key);
-            }
-        }
-        bool xflag = false;
-        if (ext) {   // extend the 16-byte tie: up to 64 bytes by the lane itself
-            int len = 16;
-#pragma unroll 1
-            for (int r = 0; r < 3; r++) {
-                uint32_t a[4], b[4];
-                lds16_unaligned(sm.win, p + len, a);
-                lds16_unaligned(sm.win, mstart + len, b);
-                const int L = prefix16(a, b);
-                len += L;
-                if (L < 16) break;
-            }
-            best = len;
-            xflag = len == 64;
-        }
-        fast_bar();
-        if (retry) clean = sm.slot2[(h >> 5) & SLOT2_MASK] == key;
-        const bool dirty = hashed && (!clean || hard);
-        if (dirty) { best = MIN_MATCH - 1; xflag = false; }
         int len = best < la ? best : la;
-        const bool is_match = len >= MIN_MATCH;   // implies idx < nact (cand)
-        if (!is_match) xflag = false;
+        const bool is_match = len >= MIN_MATCH;
         {
-            const bool stop = is_match || (dirty && idx < nact);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, stop);
-            const uint32_t b1 = __ballot_sync(0xffffffffu, (dirty && idx < nact) || xflag);
-            const uint32_t b2 = __ballot_sync(0xffffffffu, xflag);
-            const uint32_t b3 = __ballot_sync(0xffffffffu, is_match && len <= cfg.lazy && la - len >= MIN_MATCH);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, is_match), b1 = __ballot_sync(0xffffffffu, dirty);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, ext), b3 = __ballot_sync(0xffffffffu, hard);
+            const uint32_t b4 = __ballot_sync(0xffffffffu, hashed), b5 = __ballot_sync(0xffffffffu, first_in_slot && !hard);
             if (lane == 0) {
-                masks[FM_STOP * W + warp] = b0;
-                masks[FM_SPECIAL * W + warp] = b1;
-                masks[FM_X * W + warp] = b2;
-                masks[FM_SHORT * W + warp] = b3;
+                uint32_t* m = sm.fast_masks + warp * 8;
+                m[0] = b0; m[1] = b1; m[2] = b2; m[3] = b3; m[4] = b4; m[5] = b5;
             }
-            sm.fast_endl[idx] = (uint16_t)(idx + (is_match ? len : 1));   // where the parse stands after this position
+            sm.fast_endl[idx] = (uint16_t)(idx + (is_match ? len : 1));   // index of the next parse point if this is one
             sm.fast_mst[idx] = (uint16_t)mstart;
         }
         fast_bar();
-        // ---- links ----
+        uint64_t Mm, Dm, Xm, Hd, H3, Fm;
         {
-            int n1 = -1;
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                uint32_t m = masks[FM_STOP * W + w];
-                if (w < warp) m = 0;
-                else if (w == warp) m &= ~lane_lt;
-                if (n1 < 0 && m) n1 = w * 32 + __ffs(m) - 1;
+            const uint32_t* m = sm.fast_masks;
+            Mm = m[0]; Dm = m[1]; Xm = m[2]; Hd = m[3]; H3 = m[4]; Fm = m[5];
+            if (FAST_WARPS > 1) {
+                Mm |= (uint64_t)m[8] << 32; Dm |= (uint64_t)m[9] << 32; Xm |= (uint64_t)m[10] << 32;
+                Hd |= (uint64_t)m[11] << 32; H3 |= (uint64_t)m[12] << 32; Fm |= (uint64_t)m[13] << 32;
             }
-            uint32_t half = FN_NONE | (FN_NONE << 16);
-            if (n1 >= 0) {
-                uint32_t t1;
-                if ((masks[FM_SPECIAL * W + (n1 >> 5)] >> (n1 & 31)) & 1u) t1 = FN_SPECIAL;
-                else {
-                    const uint32_t e = sm.fast_endl[n1];
-                    t1 = (int)e < nact ? e : FN_NONE;
-                }
-                half = (uint32_t)n1 | (t1 << 16);
-            }
-            sm.fast_fn[idx].x = half;
-            fast_bar();
-            const uint32_t t1 = half >> 16;
-            sm.fast_fn[idx].y = t1 < FN_SPECIAL ? sm.fast_fn[t1].x : (FN_NONE | (FN_NONE << 16));
-            fast_bar();
+            Mm &= act;
+            Dm &= act;
         }
         if (stats) st_t1 = clock64();
-        // ---- rounds: walk, classify, commit; a dirty parse point is stepped literally and the walk resumes ----
-        int lo = 0;
+        // ---- resolve the greedy parse (every warp on its own, the walk is uniform): hop from match to match; the
+        // literals in between are parse points; lanes under a taken match are not, but the interior of a short one
+        // is still inserted (Deflate.Fast.cs:81-104) ----
+        int cur = 0;
+        uint64_t vis = 0, cover = 0, shortins = 0;
+        int tail_last = 0;         // last interior position of a short match that runs past the batch
+        bool hit_dirty = false;
+        const uint64_t stops = Mm | Dm;
         for (;;) {
-            uint32_t vis[W];
-#pragma unroll
-            for (int w = 0; w < W; w++) vis[w] = 0;
-            int cur = lo;
-            bool hit_dirty = false, did_x = false;
-            while (cur < nact) {
-                const uint2 f = sm.fast_fn[cur];
-                const uint32_t n1 = f.x & 0xFFFFu, t1 = f.x >> 16;
-                if (n1 == FN_NONE) { cur = nact; break; }
-                if (t1 == FN_SPECIAL) {
-                    if ((masks[FM_X * W + (n1 >> 5)] >> (n1 & 31)) & 1u) {   // long match at a parse point: the warp finishes the compare
-                        const int full = warp_extend_match(sm.win, S + (int)n1, sm.fast_mst[n1], 64, lane);
-                        const int lx = full < LA - (int)n1 ? full : LA - (int)n1;
-                        if (idx == (int)n1) { len = lx; sm.fast_endl[idx] = (uint16_t)(idx + lx); }
-                        did_x = true;
-#pragma unroll
-                        for (int w = 0; w < W; w++) vis[w] |= ((int)(n1 >> 5) == w) ? (1u << (n1 & 31)) : 0u;
-                        cur = (int)n1 + lx;
-                        continue;
-                    }
-                    cur = (int)n1;
-                    hit_dirty = true;
-                    break;
-                }
-#pragma unroll
-                for (int w = 0; w < W; w++) vis[w] |= ((int)(n1 >> 5) == w) ? (1u << (n1 & 31)) : 0u;
-                if (t1 == FN_NONE) { cur = sm.fast_endl[n1]; break; }
-                const uint32_t n2 = f.y & 0xFFFFu, t2 = f.y >> 16;
-                if (n2 == FN_NONE) { cur = nact; break; }
-                if (t2 == FN_SPECIAL) { cur = (int)t1; continue; }
-#pragma unroll
-                for (int w = 0; w < W; w++) vis[w] |= ((int)(n2 >> 5) == w) ? (1u << (n2 & 31)) : 0u;
-                if (t2 == FN_NONE) { cur = sm.fast_endl[n2]; break; }
-                cur = (int)t2;
+            const uint64_t stop = stops & (~0ull << cur);
+            if (stop == 0) { cur = nact; break; }
+            const int nxt = __ffsll((long long)stop) - 1;
+            if ((Dm >> nxt) & 1ull) { cur = nxt; hit_dirty = true; break; }
+            int e = sm.fast_endl[nxt];
+            if ((Xm >> nxt) & 1ull) {  // long match at a parse point: the warp finishes the compare
+                const int full = warp_extend_match(sm.win, S + nxt, sm.fast_mst[nxt], 16, lane);
+                const int lx = full < LA - nxt ? full : LA - nxt;
+                e = nxt + lx;
+                if (idx == nxt) len = lx;
             }
-            if (did_x) fast_bar();   // the extended lanes' fast_endl
-            // ---- classify ----
-            int np = -1, nl = -1;   // last taken match below this lane / of the round
-#pragma unroll
-            for (int w = W - 1; w >= 0; w--) {
-                uint32_t m = vis[w];
-                if (nl < 0 && m) nl = w * 32 + 31 - __clz(m);
-                if (w > warp) m = 0;
-                else if (w == warp) m &= lane_lt;
-                if (np < 0 && m) np = w * 32 + 31 - __clz(m);
-            }
-            bool covered = false, cov_short = false;
-            if (np >= 0) {
-                covered = (int)sm.fast_endl[np] > idx;
-                cov_short = covered && ((masks[FM_SHORT * W + (np >> 5)] >> (np & 31)) & 1u);
-            }
-            int tail_last = 0;   // last interior position of a short match that runs past the batch
-            if (nl >= 0 && ((masks[FM_SHORT * W + (nl >> 5)] >> (nl & 31)) & 1u)) {
-                const int e = sm.fast_endl[nl];
+            const int mlen = e - nxt;
+            vis |= 1ull << nxt;
+            const uint64_t rng = (e >= 64 ? ~0ull : (1ull << e) - 1ull) & ~((2ull << nxt) - 1ull);
+            cover |= rng;
+            if (mlen <= cfg.lazy && LA - nxt - mlen >= MIN_MATCH) {
+                shortins |= rng;
                 if (e > FAST_NB) tail_last = S + e - 1;
             }
-            const bool pp = idx >= lo && idx < cur && !covered;   // parse point
-            const bool taken = (vis[warp] >> lane) & 1u;
-            const bool ins = (pp && hashed) || cov_short;         // InsertString runs for this position
-            const uint32_t pmb = __ballot_sync(0xffffffffu, pp);
-            const uint32_t serb = __ballot_sync(0xffffffffu, ins && dirty);
-            if (lane == 0) {
-                masks[FM_PM * W + warp] = pmb;
-                masks[FM_SER * W + warp] = serb;
-            }
-            fast_bar();
-            int before = 0, nsym = 0;
-            uint32_t any_ser = 0;
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                const int c = __popc(masks[FM_PM * W + w]);
-                if (w < warp) before += c;
-                nsym += c;
-                any_ser |= masks[FM_SER * W + w];
-            }
-            // symbols (Tr_tally_*): parse points in position order
-            if (pp) {
-                const uint32_t v = taken ? ((uint32_t)(p - mstart) | ((uint32_t)(len - MIN_MATCH) << 16)) : ((scan[0] & 0xFFu) << 16);
-                o.sym[s.sym_total + before + __popc(pmb & lane_lt)] = v;
-            }
-            // InsertString of every inserted position: clean lanes side by side, then the dirty ones in position order
-            if (ins && !dirty) {
-                sm.prev[p & W_MASK] = (uint16_t)c0;
-                sm.head[h] = (uint16_t)p;
-            }
-            s.sym_total += nsym;
-            s.last_lit += nsym;
-            s.str_start = S + cur;
-            s.lookahead = LA - cur;
-            s.match_length = 0;
-            if (s.last_lit == BLOCK_SYMS) {
-                ParserState t = s;
-                if (idx == 0) close_block(t, o);
-                else { t.nblocks++; t.last_lit = 0; t.block_start = t.str_start; }
-                s = t;
-            }
-            if (any_ser != 0 || tail_last != 0 || hit_dirty) {
-                fast_bar();   // the side-by-side commits are visible to thread 0
-                if (idx == 0) {
-#pragma unroll
-                    for (int w = 0; w < W; w++)
-                        for (uint32_t m = masks[FM_SER * W + w]; m != 0; m &= m - 1)
-                            insert_string(sm, S + w * 32 + __ffs(m) - 1, hash_variant);
-                    if (tail_last != 0)
-                        for (int q = S + FAST_NB; q <= tail_last; q++) insert_string(sm, q, hash_variant);
-                    if (hit_dirty) {
-                        fast_step(sm, s, o, cfg, strategy, hash_variant);
-                        *shared_state = s;
+            cur = e;
+            if (cur >= nact) break;
+        }
+        const uint64_t done_mask = cur >= 64 ? ~0ull : (1ull << cur) - 1ull;
+        const uint64_t lanes_mask = FAST_NB >= 64 ? ~0ull : (1ull << FAST_NB) - 1ull;
+        const uint64_t pm = done_mask & ~cover & lanes_mask;             // parse points
+        const uint64_t im = ((pm & H3) | shortins) & lanes_mask;         // inserted positions
+        if (stats) st_t2 = clock64();
+        // ---- symbols (Tr_tally_*): parse points in position order ----
+        const int nsym = __popcll(pm);
+        if ((pm >> idx) & 1ull) {
+            const uint32_t v = ((vis >> idx) & 1ull) ? ((uint32_t)(p - mstart) | ((uint32_t)(len - MIN_MATCH) << 16))
+                                                     : ((scan[0] & 0xFFu) << 16);
+            o.sym[s.sym_total + __popcll(pm & below)] = v;
+        }
+        // ---- commit InsertString of every inserted position, in position order ----
+        // Threads that are the first of their hash slot go side by side.  The others (a later position of a slot already
+        // seen in the batch) follow one at a time, as the reference would execute them.
+        const uint64_t serial_ins = im & ~Fm;
+        if (((im & ~serial_ins) >> idx) & 1ull) {
+            sm.prev[p & W_MASK] = (uint16_t)c0;
+            sm.head[h] = (uint16_t)p;
+        }
+        if (serial_ins != 0) {
+            for (uint64_t m = serial_ins; m != 0; m &= m - 1) {
+                fast_bar();
+                if (idx == __ffsll((long long)m) - 1) {
+                    const int curh = sm.head[h];
+                    if (curh != p) {   // Q2
+                        sm.prev[p & W_MASK] = (uint16_t)curh;
+                        sm.head[h] = (uint16_t)p;
                     }
                 }
-                if (hit_dirty) {
-                    fast_bar();
-                    s = *shared_state;
-                }
             }
-            if (stats && idx == 0) {
-                atomicAdd(stats + 15, 1ull);
-                atomicAdd(stats + 2, hit_dirty ? 1ull : 0ull);
-                int nv = 0;
-#pragma unroll
-                for (int w = 0; w < W; w++) nv += __popc(vis[w]);
-                atomicAdd(stats + 8, (unsigned long long)nv);
-                atomicAdd(stats + 14, (unsigned long long)__popc(any_ser));
-            }
-            if (!hit_dirty) break;
-            lo = s.str_start - S;
-            if (lo >= nact) break;
         }
+        s.sym_total += nsym;
+        s.last_lit += nsym;
+        s.str_start = S + cur;
+        s.lookahead = LA - cur;
+        s.match_length = 0;
+        if (tail_last != 0) {   // the interior of a short match runs past the batch
+            fast_bar();
+            if (idx == 0)
+                for (int q = S + FAST_NB; q <= tail_last; q++) insert_string(sm, q, hash_variant);
+        }
+        if (s.last_lit == BLOCK_SYMS) {
+            ParserState t = s;
+            if (idx == 0) close_block(t, o);
+            else { t.nblocks++; t.last_lit = 0; t.block_start = t.str_start; }
+            s = t;
+        }
+        if (stats) st_t3 = clock64();
+        const bool serial = hit_dirty && ((Hd >> cur) & 1ull);
         fast_bar();   // the commits above are visible to every warp before the next batch reads head / prev
+        if (serial) {
+            if (idx == 0) {
+                fast_step(sm, s, o, cfg, strategy, hash_variant);
+                *shared_state = s;
+            }
+            fast_bar();
+            s = *shared_state;
+            fast_bar();
+        }
         if (stats && idx == 0) {
-            st_t2 = clock64();
+            const long long t4 = clock64();
             atomicAdd(stats + 0, 1ull);
-            atomicAdd(stats + 1, (unsigned long long)(s.str_start - S));
+            atomicAdd(stats + 1, (unsigned long long)cur);
+            atomicAdd(stats + 2, hit_dirty ? 1ull : 0ull);
             atomicAdd(stats + 3, (unsigned long long)nact);
             atomicAdd(stats + 4, (unsigned long long)(st_t1 - st_t0));
             atomicAdd(stats + 5, (unsigned long long)(st_t2 - st_t1));
+            atomicAdd(stats + 6, (unsigned long long)(st_t3 - st_t2));
+            atomicAdd(stats + 7, (unsigned long long)(t4 - st_t3));
+            atomicAdd(stats + 8, (unsigned long long)__popcll(vis));
+            atomicAdd(stats + 9, (unsigned long long)__popcll(Dm));
+            atomicAdd(stats + 12, (unsigned long long)__popcll(Xm & vis));
+            atomicAdd(stats + 13, serial ? 1ull : 0ull);
+            atomicAdd(stats + 14, (unsigned long long)__popcll(serial_ins));
         }
     }
     if (idx == 0) *sm.batch_seq = seq;
@@ -1092,18 +978,15 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
     sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + TILE_MAX);
     sm.tile_hh = reinterpret_cast<uint16_t*>(sm.slot + SLOT_COUNT);
     sm.fast_masks = reinterpret_cast<uint32_t*>(sm.tile_hh + TILE_MAX);
-    sm.slot2 = sm.fast_masks + 64;
-    sm.fast_fn = reinterpret_cast<uint2*>(sm.slot2 + 1024);
-    sm.fast_endl = reinterpret_cast<uint16_t*>(sm.fast_fn + 256);
-    sm.fast_mst = sm.fast_endl + 256;
-    ParserState* shared_state = reinterpret_cast<ParserState*>(sm.fast_mst + 256);
+    sm.fast_endl = reinterpret_cast<uint16_t*>(sm.fast_masks + 16);
+    sm.fast_mst = sm.fast_endl + 64;
+    ParserState* shared_state = reinterpret_cast<ParserState*>(sm.fast_mst + 64);
     int* seg_slot = reinterpret_cast<int*>(shared_state + 1);
     sm.batch_seq = reinterpret_cast<uint32_t*>(seg_slot + 1);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 1024; i += LZ_THREADS) sm.crc[i] = P.crc_tab[i];
     for (int i = tid; i < SLOT_COUNT; i += LZ_THREADS) sm.slot[i] = 0;
-    for (int i = tid; i < 1024; i += LZ_THREADS) sm.slot2[i] = 0;
     if (tid == 0) *sm.batch_seq = 0;
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -1311,10 +1194,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
 
 size_t lz77_smem_bytes()
 {
-    // window | head | prev | crc | mbarrier | adler reduction | tile_rec | slot | tile_hh | fast_masks | slot2 | fast_fn |
-    // fast_endl | fast_mst | ParserState | seg_slot, batch_seq | slack
-    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + TILE_MAX * 8 + SLOT_COUNT * 4 +
-           TILE_MAX * 2 + 64 * 4 + 1024 * 4 + 256 * 8 + 256 * 2 + 256 * 2 + sizeof(ParserState) + 16 + 64;
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 256 * 8 + 256 * 2 + 64 + 128 + 128;
 }
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)

@@ -181,3 +181,33 @@ def test_large_property_round_trip(engine):
     dec = torch.empty(n, dtype=torch.uint8, device="cuda")
     dl, dad = engine.inflate_segments_device(out.data_ptr(), out_len, ends.data_ptr(), n // ss, ss, dec.data_ptr(), n)
     assert dl == n and dad == adler and torch.equal(dec, data)
+
+
+def _run_lengths_data(seed, n):
+    """Runs of every length around the Rle thresholds (1..3, 257..262, 515..520, long), separated by distinct bytes."""
+    rng = np.random.RandomState(seed)
+    out = bytearray()
+    lens = list(range(1, 8)) + list(range(255, 264)) + list(range(513, 522)) + [1000, 5000, 40000]
+    while len(out) < n:
+        r = int(lens[rng.randint(len(lens))])
+        b = int(rng.randint(256))
+        if out and out[-1] == b:
+            b = (b + 1) & 255
+        out += bytes([b]) * r
+        if rng.randint(3) == 0:
+            out += rng.bytes(int(rng.randint(1, 40)))
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("ss", [65536, 262144])
+def test_parallel_symbolizer_rle_and_huffman_only(engine, oracle, ss):
+    """zsb_symbolize.cu: Rle run arithmetic (remainders below 3, exact multiples of 258, runs across segment boundaries,
+    Q14), HuffmanOnly with both parsers, block cuts at 16383 symbols incl. the empty trailing block, buf_valid."""
+    nolit = bytes((i * 7 + (i >> 8)) & 255 for i in range(ss + 2 * 16383))          # no equal neighbours: symbols == bytes
+    cases = [_run_lengths_data(1, 3 * ss + 12345), _run_lengths_data(2, ss), bytes(2 * ss + 777), b"\x07" * (ss + 259),
+             nolit, nolit[:ss + 16383], np.random.RandomState(5).bytes(ss + 100), b"ab" * 40000 + bytes(3) + b"c" * 70000]
+    for data in cases:
+        for level, strategy in ((6, 3), (1, 3), (6, 2), (1, 2)):
+            want, want_ends, want_adler = oracle.deflate_segments(data, ss, level, strategy)
+            got, ends, adler = engine.deflate_segments(data, ss, level, strategy)
+            assert got == want and ends == want_ends and adler == want_adler, (len(data), level, strategy)

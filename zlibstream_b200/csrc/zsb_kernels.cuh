@@ -27,6 +27,9 @@ struct Lz77Params {
 };
 size_t lz77_smem_bytes();
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream);
+// HuffmanOnly and Rle need no hash chains: zsb_symbolize.cu produces their symbols, blocks and Adler sums in parallel.
+bool symbolize_applies(const Lz77Params& P);
+cudaError_t launch_symbolize(const Lz77Params& P, int num_sms, cudaStream_t stream);
 
 // ---- Huffman stage (zsb_huffman.cu) --------------------------------------------------------------
 constexpr int kHdrWords = 80;   // dynamic tree description: <= 14 + 57 + 316 * 7 bits

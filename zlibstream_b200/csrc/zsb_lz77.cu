@@ -12,6 +12,8 @@
 // staged window so the checksum costs no extra HBM pass.
 #include "zsb_kernels.cuh"
 
+#include <cstdlib>
+
 namespace zsb {
 
 namespace {
@@ -1199,6 +1201,9 @@ size_t lz77_smem_bytes()
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
 {
+    // ZSB_NO_SYMBOLIZE=1 keeps HuffmanOnly / Rle on the serial path below (A/B measurements, parity cross-checks)
+    static const bool no_symbolize = getenv("ZSB_NO_SYMBOLIZE") != nullptr;
+    if (!no_symbolize && !P.stats && symbolize_applies(P)) return launch_symbolize(P, num_sms, stream);
     static bool configured = false;
     size_t smem = lz77_smem_bytes();
     if (!configured) {

@@ -10,6 +10,17 @@ import corpus_data
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "warp", "lanes"], autouse=True)
+def inflate_kernel(request, monkeypatch):
+    """The library picks the warp-per-segment or the lane-per-segment inflate kernel from the number of segments; the
+    parity tests run with the automatic choice and with each kernel forced (ZSB_INFLATE_KERNEL is read per call)."""
+    if request.param == "auto":
+        monkeypatch.delenv("ZSB_INFLATE_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("ZSB_INFLATE_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n", [1, 8, 215, 1024, 1024 + 15, 2034, 4096, 5552, 5553, 65535, 65536, 65537, (1 << 22) + 13])
 def test_adler32_matches_zlib(engine, n):
     d = np.random.RandomState(1).bytes(n)                  # Adler32Tests.cs:22-40 lengths and beyond

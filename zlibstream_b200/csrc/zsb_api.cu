@@ -606,15 +606,16 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
     unsigned int* d_carry_flag = reinterpret_cast<unsigned int*>(small + 20);
     CU(cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned int), st));
-    // ZSB_INFLATE_KERNEL=warp selects the older warp-per-segment kernel (A/B measurements); default: lane per segment
-    static const bool use_lanes = [] {
+    // Two kernels (profiles/r01i_inflate_sweep.txt): a warp per segment decodes one segment fastest and wins while the
+    // segments are few; a lane per segment shares every issued instruction 32 ways and wins once there are enough
+    // segments to fill the SMs' resident warps.  ZSB_INFLATE_KERNEL=warp|lanes forces one of them.
+    const int forced_kernel = [] {   // read per call: the tests switch kernels at run time
         const char* e = getenv("ZSB_INFLATE_KERNEL");
-        return !(e && strcmp(e, "warp") == 0);
+        return !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : 0;
     }();
-    if (use_lanes) {
-        CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
-        CU(ctx->inf_carry.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
-    }
+    const bool use_lanes = forced_kernel ? forced_kernel == 2 : nseg >= (size_t)ctx->num_sms * 168;
+    if (use_lanes) CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
+    CU(ctx->inf_carry.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
 
     InflateParams I;
     I.in = d_in;
@@ -629,10 +630,8 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     I.seg_adler = nullptr;
     I.seg_status = ctx->inf_status.as<int>();
     I.work_counter = d_work;
-    if (use_lanes) {
-        I.seg_carry = ctx->inf_carry.as<uint32_t>();
-        I.carry_flag = d_carry_flag;
-    }
+    I.seg_carry = ctx->inf_carry.as<uint32_t>();
+    I.carry_flag = d_carry_flag;
     timing_mark(ctx, 2, true);
     if (use_lanes) CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
     else CU(launch_inflate(I, ctx->num_sms, st));
@@ -643,7 +642,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     uint32_t got_adler = 1;
     uint8_t trailer[6] = {0};
     unsigned int carry_flag = 0;
-    if (use_lanes) CU(cudaMemcpyAsync(&carry_flag, d_carry_flag, sizeof carry_flag, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&carry_flag, d_carry_flag, sizeof carry_flag, cudaMemcpyDeviceToHost, st));
     if (nseg) {
         CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

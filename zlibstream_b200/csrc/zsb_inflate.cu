@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
         const uint32_t o_cap = (uint32_t)((P.out_cap - o_begin) < P.seg_size ? (P.out_cap - o_begin) : P.seg_size);
         uint8_t* out = P.out + o_begin;
         uint32_t o = 0;
+        uint32_t carry = 0;   // Q14: leading bytes that repeat the previous segment's last byte (Rle streams)
         int err = IE_OK;
         uint32_t pend_at = 0;     // a short match copy whose loads are in flight (stores still to be issued)
         int pend_len = 0;
@@ -398,8 +399,17 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                 if (op == OP_EOB) break;
                 if (op == OP_ERR) { err = (int)((packed >> 2) & 0x3ffu); break; }
                 const int a = (int)((packed >> 2) & 0x3ffu), d = (int)(packed >> 12);
-                if ((uint32_t)d > o) { err = IE_DIST_TOO_FAR; break; }
                 if (o + (uint32_t)a > o_cap) { err = IE_OUTPUT_OVERFLOW; break; }
+                if ((uint32_t)d > o || o - (uint32_t)d < carry) {
+                    // Q14 (Deflate.Rle.cs:47-50): distance-1 runs of the previous segment's last byte open the segment;
+                    // placeholders now, inflate_carry_fixup_kernel fills them in once every segment is decoded
+                    if (!(d == 1 && o == carry && seg > 0)) { err = IE_DIST_TOO_FAR; break; }
+                    for (int i = lane; i < a; i += GW) out[o + i] = 0;
+                    carry += (uint32_t)a;
+                    o += (uint32_t)a;
+                    __syncwarp(gmask);
+                    continue;
+                }
                 // out[o + i] = out[o - d + (i mod d)]: every source byte was written before this match
                 if (a <= PEND_MAX) {
 #pragma unroll
@@ -430,6 +440,8 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
         if (lane == 0) {
             P.seg_out_len[seg] = (uint32_t)o;
             P.seg_status[seg] = err;
+            if (P.seg_carry) P.seg_carry[seg] = carry;
+            if (carry && P.carry_flag) *P.carry_flag = 1;
         }
         __syncwarp(gmask);
     }

@@ -154,7 +154,7 @@ cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* s
         attr_set = true;
     }
     // Segments per warp: as many as still leave ~kWarpsWanted warps per SM (ZSB_INFLATE_SEGS_PER_WARP overrides).
-    static const int forced = [] {
+    const int forced = [] {
         const char* e = getenv("ZSB_INFLATE_SEGS_PER_WARP");
         const int v = e ? atoi(e) : 0;
         return v >= 1 && v <= 32 ? v : 0;

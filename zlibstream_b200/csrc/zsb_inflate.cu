@@ -48,28 +48,24 @@ struct BitReader {   // lane 0 only; positions are relative to the segment's fir
     uint32_t pos;        // offset of the next byte to load
     uint32_t end;        // the segment's compressed size
     uint32_t limit;      // bytes that may be loaded (to the end of the whole compressed buffer, capped)
-    uint32_t fast_end;   // pos < fast_end <=> pos + 16 <= limit: two aligned 64-bit loads stay in bounds
     uint64_t acc;
     int nbits;
-    // Refill to >= 56 bits from two aligned 64-bit loads; bytes past `end` (the next segment's) may enter the
+    // Call with nbits <= 32: one aligned 32-bit load brings the accumulator to >= 33 bits (7 instructions; the earlier
+    // two-word 64-bit refill cost 23 and ran on 41 % of the symbols).  Bytes past `end` (the next segment's) may enter the
     // accumulator but are never consumed by a well-formed segment -- consumption is checked against `end` at every
-    // block boundary.
+    // block boundary.  Unaligned starts (segment start, after a stored block) and the last bytes of the buffer go bytewise.
     __device__ __forceinline__ void refill()
     {
-        if (pos < fast_end) {
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + pos);
-            const uint64_t* q = reinterpret_cast<const uint64_t*>(addr & ~(uintptr_t)7);
-            const uint64_t a = __ldg(q), b = __ldg(q + 1);
-            const int sh = (int)(addr & 7) * 8;
-            const uint64_t w = sh ? (a >> sh) | (b << (64 - sh)) : a;
-            acc |= w << nbits;
-            const int adv = (63 - nbits) >> 3;
-            pos += (uint32_t)adv;
-            nbits += adv * 8;
+        const uint8_t* p = in + pos;
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0 && pos + 4 <= limit) {
+            acc |= (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(p)) << nbits;
+            pos += 4;
+            nbits += 32;
         } else {
             while (nbits <= 56 && pos < limit) {
                 acc |= (uint64_t)in[pos++] << nbits;
                 nbits += 8;
+                if (nbits > 32 && (reinterpret_cast<uintptr_t>(in + pos) & 3u) == 0) break;
             }
         }
     }
@@ -149,7 +145,7 @@ __device__ int build_table(WarpTables& t, int base, int n, bool dist, int lane, 
 __device__ __forceinline__ int decode_sym(BitReader& b, const uint16_t* fast, int fast_bits, const uint16_t* count,
                                           const uint16_t* first, const uint16_t* offset, const uint16_t* sorted)
 {
-    if (b.nbits < 32) b.refill();
+    if (b.nbits <= 32) b.refill();
     const uint32_t e = fast[b.acc & ((1u << fast_bits) - 1)];
     if (e) {
         const int len = (int)(e & 15);
@@ -213,7 +209,6 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
             const uint64_t room = P.n - c_begin;
             br.limit = room > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)room;
         }
-        br.fast_end = br.limit >= 16 ? br.limit - 15 : 0;
 
         // blocks until the segment's compressed bytes are used up (it ends with the full-flush marker)
         while (err == IE_OK) {
@@ -340,7 +335,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                 if (lane == 0) {
                     int op = OP_ERR, a = IE_BAD_LCODE, d = 0;
                     for (;;) {
-                        if (br.nbits < 48) br.refill();
+                        if (br.nbits <= 32) br.refill();   // >= 33 bits: a literal/length code (<= 15) and its extra bits (<= 5)
                         uint32_t e = t.fast_l[br.acc & ((1u << FAST_L) - 1)];
                         int sym;
                         if (e) {
@@ -362,6 +357,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                         const int len = c_len_base[ls] + (int)br.peek(eb);
                         br.drop(eb);
                         int ds;
+                        if (br.nbits <= 32) br.refill();   // >= 33 bits: a distance code (<= 15) and its extra bits (<= 13)
                         e = t.fast_d[br.acc & ((1u << FAST_D) - 1)];
                         if (e) {
                             br.drop((int)(e & 15));

@@ -44,6 +44,11 @@ struct Smem {
     uint32_t* batch_seq;
     uint16_t* tile_hh;   // TILE_MAX: what InsertString returned for each position of the current DeflateSlow tile
     uint2* tile_rec;     // TILE_MAX: Longest_match results of the tile (full / quarter chain budget)
+    // pipelined DeflateSlow (1024-thread kernel): tiles lie on a fixed grid up to pipe_ins_limit and are inserted / searched
+    // by producer warps while warp 0 replays; pipe_flags[0] = tiles produced, [1] = tiles consumed.  0 / nullptr otherwise.
+    int pipe_ins_limit;
+    int pipe_ntiles;
+    volatile int* pipe_flags;
     uint32_t* fast_masks; // 2 * 8 ballots of the DeflateFast batch (per warp)
     uint16_t* fast_endl;  // 64: next parse point of each batch position if it is one
     uint16_t* fast_mst;   // 64: match start of each batch position
@@ -649,6 +654,105 @@ __device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const Le
     return make_uint2(full, have_early ? early : full);
 }
 
+// (B) with FOUR threads per position (a quad of adjacent lanes), for the 1024-thread kernel.  Longest_match's outcome
+// depends only on the common-prefix lengths L_1, L_2, ... of the candidates in chain order: it is the first candidate with
+// L >= nice_match if there is one within the budget, else the longest one (the earliest among equals); the pre-filters
+// only skip candidates that cannot beat the running best.  So lane q of the quad walks the whole chain (links are one
+// dependent shared-memory load each) but compares only candidates q+1, q+5, q+9, ... against ITS OWN running best (a
+// candidate that cannot beat the lane's best cannot beat the quad's), and the quad merges: minimum step with L >= nice,
+// else maximum L with the smallest step.  One iteration = four chain steps.  The result for the reduced budget
+// (chain >> 2, a multiple of 4 at every level) is the merge after that many steps.
+// Measured (profiles/r01i_config_sweep.jsonl vs r01j): 1.6x faster than one thread per position at level 9, 1.1-1.2x at
+// level 6 on mixed and PNG-like data (long compares split four ways), 0.9x on text-like level 6 (short compares: the
+// replicated chain walk costs more than it saves).  A variant where only lane 0 walks the chain and shuffles the
+// candidates out, with a one-byte pre-filter, was slower everywhere: the phase is bound by issued instructions
+// (~100 per four steps), not by shared-memory wavefronts (13 % of the pipe).
+__device__ void slow_tile_search_quad(const Smem& sm, int S, int idx, const LevelCfg& cfg)
+{
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const uint32_t qmask = 0xFu << (lane & ~3);
+    const int p = S + idx;
+    const int hash_head = sm.tile_hh[idx];
+    int best = MIN_MATCH - 1, ms = 0, bstep = 0x7fffffff;       // this lane's best candidate and the step it was met at
+    int nice_step = 0x7fffffff;                                 // first step (of this lane) with L >= nice
+    uint32_t early = 0;
+    bool have_early = false;
+    if (hash_head != 0 && p - hash_head <= MAX_DIST) {          // uniform across the quad
+        const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
+        const int early_budget = cfg.chain >> 2;
+        int cur = hash_head, step = 0, chain = cfg.chain;       // `cur` = candidate of step `step + 1`; same in all four lanes
+        bool alive = true;
+        while (alive) {
+            // candidates of steps step+1 .. step+4: lane q takes the (q+1)-th, all lanes end up at the fifth
+            int mine = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (alive) {
+                    if (cur >= p) alive = false;
+                    else {
+                        if (k == q) mine = cur;
+                        const int nxt = sm.prev[cur & W_MASK];
+                        step++;
+                        cur = nxt;
+                        if (!(cur > limit && --chain != 0)) alive = false;   // the walk ends after this candidate
+                    }
+                }
+            }
+            const int my_step = step - ((step - 1) & 3) + q;    // this iteration's candidates are steps base + 1 .. base + 4
+            if (mine) {
+                const int off = best >= 3 ? best - 3 : 0;
+                const uint32_t mask = best >= 3 ? 0xffffffffu : 0x00ffffffu;
+                if (((lds_u32_unaligned(sm.win, mine + off) ^ lds_u32_unaligned(sm.win, p + off)) & mask) == 0) {
+                    const int L = common_prefix258(sm.win, p, mine);
+                    if (L > best) {
+                        best = L;
+                        ms = mine;
+                        bstep = my_step;
+                        if (L >= cfg.nice && nice_step == 0x7fffffff) nice_step = my_step;
+                    }
+                }
+            }
+            // a candidate with L >= nice ends the reference's walk
+            if (__any_sync(qmask, nice_step != 0x7fffffff)) break;
+            if (step == early_budget && alive) {                // snapshot for the reduced budget (no break happened so far)
+                int b = best, st = bstep, m = ms;
+#pragma unroll
+                for (int d = 1; d < 4; d <<= 1) {
+                    const int ob = __shfl_xor_sync(qmask, b, d), ost = __shfl_xor_sync(qmask, st, d), om = __shfl_xor_sync(qmask, m, d);
+                    if (ob > b || (ob == b && ost < st)) { b = ob; st = ost; m = om; }
+                }
+                early = (uint32_t)b | ((uint32_t)(b > MIN_MATCH - 1 ? m : 0) << 9);
+                have_early = true;
+            }
+        }
+    }
+    // merge: the first step with L >= nice wins outright; candidates met after it do not count
+    int ns = nice_step;
+#pragma unroll
+    for (int d = 1; d < 4; d <<= 1) ns = min(ns, __shfl_xor_sync(qmask, ns, d));
+    int b = best, st = bstep, m = ms;
+    if (st > ns) { b = MIN_MATCH - 1; st = 0x7fffffff; m = 0; }   // only possible for a best found in the final iteration
+#pragma unroll
+    for (int d = 1; d < 4; d <<= 1) {
+        const int ob = __shfl_xor_sync(qmask, b, d), ost = __shfl_xor_sync(qmask, st, d), om = __shfl_xor_sync(qmask, m, d);
+        if (ob > b || (ob == b && ost < st)) { b = ob; st = ost; m = om; }
+    }
+    if (q == 0) {
+        const uint32_t full = (uint32_t)b | ((uint32_t)(b > MIN_MATCH - 1 ? m : 0) << 9);
+        sm.tile_rec[idx] = make_uint2(full, have_early ? early : full);
+    }
+}
+
+// Before the replay inserts a position itself (one past the pre-inserted region), every producer tile must be done:
+// InsertString calls have to happen in position order.
+__device__ __forceinline__ void pipe_wait_all(const Smem& sm)
+{
+    if (sm.pipe_flags) {
+        while (sm.pipe_flags[0] < sm.pipe_ntiles) __nanosleep(100);
+        __threadfence_block();
+    }
+}
+
 // (C): DeflateSlow (Deflate.Slow.cs:18-159) over the tile [S, S + T), Longest_match / InsertString looked up.
 __device__ void slow_tile_replay(const Smem& sm, ParserState& s, const SegOut& o, const LevelCfg& cfg, int strategy,
                                  int hash_variant, int S, int T, int until)
@@ -683,7 +787,14 @@ __device__ void slow_tile_replay(const Smem& sm, ParserState& s, const SegOut& o
             s.prev_length -= 2;
             do {
                 if (++s.str_start <= max_insert)
-                    hash_head = s.str_start < tile_end ? (int)sm.tile_hh[s.str_start - S] : insert_string(sm, s.str_start, hash_variant);
+                {
+                    if (s.str_start < tile_end) hash_head = (int)sm.tile_hh[s.str_start - S];
+                    else if (s.str_start < sm.pipe_ins_limit) hash_head = 0;   // a producer warp inserts it (value unused: the next visit reloads it)
+                    else {
+                        pipe_wait_all(sm);
+                        hash_head = insert_string(sm, s.str_start, hash_variant);
+                    }
+                }
             } while (--s.prev_length != 0);
             s.match_available = 0;
             s.match_length = MIN_MATCH - 1;
@@ -719,7 +830,7 @@ __device__ void slow_tile_replay_warp(const Smem& sm, ParserState& s, const SegO
     const int lane = threadIdx.x & 31;
     const uint32_t below = (1u << lane) - 1u;
     const int tile_end = S + T;
-    int ins_done_to = tile_end;   // positions >= tile_end below this one have been inserted
+    int ins_done_to = tile_end > sm.pipe_ins_limit ? tile_end : sm.pipe_ins_limit;   // positions >= tile_end below this one have been (or will be, by a producer) inserted
     while (s.str_start < tile_end) {
         const int g0 = s.str_start;
         const int gn = tile_end - g0 < 32 ? tile_end - g0 : 32;
@@ -816,8 +927,10 @@ __device__ void slow_tile_replay_warp(const Smem& sm, ParserState& s, const SegO
         s.match_available = avail;
     }
     if (s.str_start > ins_done_to) {   // positions past the tile that the last match skipped over (Deflate.Slow.cs:98-105)
-        if (lane == 0)
+        if (lane == 0) {
+            pipe_wait_all(sm);
             for (int q = ins_done_to; q < s.str_start; q++) insert_string(sm, q, hash_variant);
+        }
         __syncwarp();
     }
 }
@@ -900,6 +1013,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 }
 
 // Cooperative copy of n bytes global -> shared; uses the bulk-copy engine for the 16-byte aligned body.
+template <int NT>
 __device__ void stage_input(uint8_t* dst, const uint8_t* src, int n, uint64_t* bar, uint32_t& phase)
 {
     const int tid = threadIdx.x;
@@ -911,7 +1025,7 @@ __device__ void stage_input(uint8_t* dst, const uint8_t* src, int n, uint64_t* b
             bulk_g2s(dst, src, (uint32_t)body, bar);
         }
     }
-    for (int i = body + tid; i < n; i += LZ_THREADS) dst[i] = src[i];
+    for (int i = body + tid; i < n; i += NT) dst[i] = src[i];
     if (body > 0) {
         mbar_wait(bar, phase);
         phase ^= 1;
@@ -919,11 +1033,12 @@ __device__ void stage_input(uint8_t* dst, const uint8_t* src, int n, uint64_t* b
 }
 
 // Partial Adler sums of n staged bytes: s1 = sum b, s2 = sum (n - j) * b_j   (Adler32.cs:270-326 unrolled)
+template <int NT>
 __device__ void adler_chunk(const uint8_t* p, int n, uint32_t* red, uint32_t& a, uint32_t& b)
 {
     const int tid = threadIdx.x;
     unsigned long long s1 = 0, s2 = 0;
-    for (int i = tid * 4; i < n; i += LZ_THREADS * 4) {
+    for (int i = tid * 4; i < n; i += NT * 4) {
         if (i + 4 <= n && ((reinterpret_cast<uintptr_t>(p + i) & 3) == 0)) {
             uint32_t v = *reinterpret_cast<const uint32_t*>(p + i);
             uint32_t b0 = v & 0xFF, b1 = (v >> 8) & 0xFF, b2 = (v >> 16) & 0xFF, b3 = v >> 24;
@@ -952,7 +1067,7 @@ __device__ void adler_chunk(const uint8_t* p, int n, uint32_t* red, uint32_t& a,
     __syncthreads();
     if (tid == 0) {
         unsigned long long t1 = 0, t2 = 0;
-        for (int w = 0; w < LZ_THREADS / 32; w++) {
+        for (int w = 0; w < NT / 32; w++) {
             t1 += r64[w * 2];
             t2 += r64[w * 2 + 1];
         }
@@ -966,8 +1081,12 @@ __device__ void adler_chunk(const uint8_t* p, int n, uint32_t* red, uint32_t& a,
 
 }  // namespace
 
-__global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params P)
+// NT = 256: every parser (DeflateFast needs the registers).  NT = 1024, SLOW_ONLY: levels 4-9, where the tile search runs
+// four threads per position (slow_tile_search_quad) and 32 warps hide the shared-memory latency of the chain walks.
+template <int NT, bool SLOW_ONLY>
+__global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
 {
+    constexpr int LZ_THREADS = NT;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem sm;
     sm.win = smem_raw;
@@ -976,15 +1095,19 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
     sm.crc = sm.prev + W_SIZE;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm.crc + 1024);
     uint32_t* red = reinterpret_cast<uint32_t*>(bar + 1);  // 2 * 8 * u64
-    sm.tile_rec = reinterpret_cast<uint2*>(red + 64);
-    sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + TILE_MAX);
+    sm.tile_rec = reinterpret_cast<uint2*>(red + 128);
+    sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + 3 * TILE_MAX);   // three tile buffers (pipelined DeflateSlow)
     sm.tile_hh = reinterpret_cast<uint16_t*>(sm.slot + SLOT_COUNT);
-    sm.fast_masks = reinterpret_cast<uint32_t*>(sm.tile_hh + TILE_MAX);
+    sm.fast_masks = reinterpret_cast<uint32_t*>(sm.tile_hh + 3 * TILE_MAX);
     sm.fast_endl = reinterpret_cast<uint16_t*>(sm.fast_masks + 16);
     sm.fast_mst = sm.fast_endl + 64;
     ParserState* shared_state = reinterpret_cast<ParserState*>(sm.fast_mst + 64);
     int* seg_slot = reinterpret_cast<int*>(shared_state + 1);
     sm.batch_seq = reinterpret_cast<uint32_t*>(seg_slot + 1);
+    volatile int* pipe_flags = reinterpret_cast<volatile int*>(sm.batch_seq + 1);   // 2 ints
+    sm.pipe_ins_limit = 0;
+    sm.pipe_ntiles = 0;
+    sm.pipe_flags = nullptr;
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 1024; i += LZ_THREADS) sm.crc[i] = P.crc_tab[i];
@@ -996,6 +1119,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
 
     LevelCfg cfg;
     cfg.good = P.good; cfg.lazy = P.lazy; cfg.nice = P.nice; cfg.chain = P.chain; cfg.fn = P.fn;
+    if (SLOW_ONLY) cfg.fn = FN_SLOW;
 
     for (;;) {
         if (tid == 0) *seg_slot = (int)atomicAdd(P.work_counter, 1u);
@@ -1102,9 +1226,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                         }
                         if (avail_in == 0) break;
                         int n = avail_in < more ? avail_in : more;
-                        stage_input(sm.win + str_start + lookahead, seg_in + in_pos, n, bar, phase);
+                        stage_input<NT>(sm.win + str_start + lookahead, seg_in + in_pos, n, bar, phase);
                         __syncthreads();
-                        adler_chunk(sm.win + str_start + lookahead, n, red, adler_a, adler_b);
+                        adler_chunk<NT>(sm.win + str_start + lookahead, n, red, adler_a, adler_b);
                         avail_in -= n;
                         in_pos += n;
                         lookahead += n;
@@ -1123,13 +1247,75 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
             }
             const long long st_f1 = P.stats ? clock64() : 0;
             // ---- parse until the next refill / slide or the end of the segment ----
-            if (cfg.fn == FN_FAST) {
+            if (!SLOW_ONLY && cfg.fn == FN_FAST) {
                 if (tid < FAST_NB) {
                     ParserState s = *shared_state;
                     fast_bar();
                     parse_fast_multi(sm, s, shared_state, o, cfg, P.strategy, P.hash_variant, P.stats);
                     fast_bar();
                     if (tid == 0) *shared_state = s;
+                }
+            } else if (cfg.fn == FN_SLOW && NT == 1024 && P.strategy != 2 && !P.stats && cfg.chain <= 128) {
+                // Levels 4-6 only: on a fixed tile grid every position below L is searched, whereas the tile-at-a-time loop
+                // below starts each tile where the parse stands and so never searches what a match that crossed the tile
+                // end skipped -- worth more than the overlap when the search dominates (level 9, mixed data: 2.8 s vs 3.3 s
+                // per 256 MiB).
+                // ---- pipelined tiles: warp 0 replays tile k while warps 1..31 insert and search tile k + 1 -----------------
+                constexpr int TP = 248;   // positions per tile: 31 producer warps x 8 quads
+                const int S0 = shared_state->str_start;
+                const int avail = shared_state->lookahead - (MIN_LOOKAHEAD - 1);
+                if (tid == 0) { pipe_flags[0] = 0; pipe_flags[1] = 0; }
+                __syncthreads();
+                if (avail < 16) {   // too close to a refill / the end of the segment: the reference loop, literally
+                    if (tid == 0) {
+                        ParserState s = *shared_state;
+                        parse_slow(sm, s, o, cfg, P.strategy, P.hash_variant);
+                        *shared_state = s;
+                    }
+                } else {
+                    const int L = S0 + avail, ntiles = (avail + TP - 1) / TP;
+                    Smem smb = sm;
+                    smb.pipe_ins_limit = L;
+                    smb.pipe_ntiles = ntiles;
+                    smb.pipe_flags = pipe_flags;
+                    if (tid < 32) {
+                        ParserState s = *shared_state;
+                        for (int k = 0; k < ntiles; k++) {
+                            const int tS = S0 + k * TP, tT = L - tS < TP ? L - tS : TP;
+                            if (tid == 0) while (pipe_flags[0] < k + 1) __nanosleep(100);   // back off: a spinning warp takes issue slots from the producers
+                            __syncwarp();
+                            __threadfence_block();
+                            smb.tile_rec = sm.tile_rec + (k % 3) * TILE_MAX;
+                            smb.tile_hh = sm.tile_hh + (k % 3) * TILE_MAX;
+                            if (s.str_start < tS + tT) slow_tile_replay_warp(smb, s, o, cfg, P.strategy, P.hash_variant, tS, tT);
+                            __syncwarp();
+                            if (tid == 0) {
+                                __threadfence_block();
+                                pipe_flags[1] = k + 1;
+                            }
+                        }
+                        if (tid == 0) *shared_state = s;
+                    } else {
+                        const int ptid = tid - 32;
+                        for (int k = 0; k < ntiles; k++) {
+                            const int tS = S0 + k * TP, tT = L - tS < TP ? L - tS : TP;
+                            // Three buffers: tile k reuses the buffer of tile k - 3.  Two would deadlock when a match that starts in
+                            // tile n - 3 runs past the last (short) tile: the replay then waits for every tile (pipe_wait_all) while
+                            // the last tile would wait for the replay to leave tile n - 3.
+                            if (ptid == 0 && k >= 3) while (pipe_flags[1] < k - 2) __nanosleep(100);
+                            asm volatile("bar.sync 3, 992;" ::: "memory");
+                            smb.tile_rec = sm.tile_rec + (k % 3) * TILE_MAX;
+                            smb.tile_hh = sm.tile_hh + (k % 3) * TILE_MAX;
+                            if (ptid < 32) slow_tile_insert(smb, tS, tT, P.hash_variant);
+                            asm volatile("bar.sync 3, 992;" ::: "memory");
+                            if (ptid < 4 * tT) slow_tile_search_quad(smb, tS, ptid >> 2, cfg);
+                            asm volatile("bar.sync 3, 992;" ::: "memory");
+                            if (ptid == 0) {
+                                __threadfence_block();
+                                pipe_flags[0] = k + 1;
+                            }
+                        }
+                    }
                 }
             } else if (cfg.fn == FN_SLOW) {
                 for (;;) {
@@ -1153,7 +1339,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                     }
                     const long long tB = P.stats ? clock64() : 0;
                     if (P.strategy != 2) {
-                        if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
+                        if (NT >= 4 * TILE_MAX) {
+                            if (tid < 4 * T) slow_tile_search_quad(sm, S, tid >> 2, cfg);
+                        } else if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
                         __syncthreads();
                     }
                     const long long tC = P.stats ? clock64() : 0;
@@ -1174,7 +1362,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
                         atomicAdd(P.stats + 6, (unsigned long long)(clock64() - tC));
                     }
                 }
-            } else if (tid == 0) {
+            } else if (!SLOW_ONLY && tid == 0) {
                 ParserState s = *shared_state;
                 parse_rle(sm, s, o);
                 *shared_state = s;
@@ -1196,7 +1384,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) lz77_segments_kernel(Lz77Params
 
 size_t lz77_smem_bytes()
 {
-    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 64 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 256 * 8 + 256 * 2 + 64 + 128 + 128;
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 128 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 768 * 8 + 768 * 2 + 64 + 128 + 128;
 }
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
@@ -1207,13 +1395,21 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
     static bool configured = false;
     size_t smem = lz77_smem_bytes();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lz77_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(lz77_segments_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(lz77_segments_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     int grid = (int)(P.nseg < (uint32_t)num_sms ? P.nseg : (uint32_t)num_sms);
     if (grid < 1) grid = 1;
-    lz77_segments_kernel<<<grid, LZ_THREADS, smem, stream>>>(P);
+    // ZSB_SLOW_THREADS=256 keeps levels 4-9 on the 256-thread kernel (A/B measurements)
+    static const bool slow_wide = [] {
+        const char* e = getenv("ZSB_SLOW_THREADS");
+        return !(e && atoi(e) == 256);
+    }();
+    if (P.fn == FN_SLOW && slow_wide) lz77_segments_kernel<1024, true><<<grid, 1024, smem, stream>>>(P);
+    else lz77_segments_kernel<256, false><<<grid, 256, smem, stream>>>(P);
     return cudaGetLastError();
 }
 

@@ -23,6 +23,9 @@ constexpr int WIN_PAD = 64;
 constexpr int SLOT_COUNT = 4096;
 constexpr int TILE_MAX = 256;   // positions per DeflateSlow tile (= LZ_THREADS, < MIN_LOOKAHEAD)
 constexpr uint32_t SLOT_MASK = SLOT_COUNT - 1;
+constexpr int WIDE_TILE = 992;        // positions per tile of the pipelined DeflateSlow: one per thread of 31 producer warps
+constexpr int WIDE_SLOTS = 1024;      // slot table of the 1024-thread kernel (only slow_tile_insert uses it there)
+constexpr int SHADOW_N = 1024;        // >= WIDE_TILE, power of two
 
 struct ParserState {
     int str_start, lookahead, block_start, match_length, prev_length, match_start, prev_match, match_available;
@@ -49,6 +52,11 @@ struct Smem {
     int pipe_ins_limit;
     int pipe_ntiles;
     volatile int* pipe_flags;
+    uint32_t slot_mask;   // entries of `slot` - 1
+    // prev[] slots overwritten by the inserts of the current wide tile keep their old value here (index: position & 1023),
+    // so that a search may run after MORE than MIN_LOOKAHEAD later positions have been inserted.  nullptr otherwise.
+    uint16_t* shadow;
+    int shadow_lo, shadow_hi;   // the tile [lo, hi) whose inserts the shadow covers
     uint32_t* fast_masks; // 2 * 8 ballots of the DeflateFast batch (per warp)
     uint16_t* fast_endl;  // 64: next parse point of each batch position if it is one
     uint16_t* fast_mst;   // 64: match start of each batch position
@@ -318,11 +326,11 @@ __device__ void parse_fast_multi(const Smem& sm, ParserState& s, ParserState* sh
         const uint32_t key = (seq << 6) | (uint32_t)(63 - idx);
         if (hashed) {
             h = hash_of(sm, __funnelshift_r(scan[0], scan[1], 16), hash_variant);
-            atomicMax(&sm.slot[h & SLOT_MASK], key);
+            atomicMax(&sm.slot[h & sm.slot_mask], key);
             c0 = sm.head[h];
         }
         fast_bar();
-        if (hashed) first_in_slot = sm.slot[h & SLOT_MASK] == key;
+        if (hashed) first_in_slot = sm.slot[h & sm.slot_mask] == key;
         const bool hard = hashed && c0 >= p;                 // Q2/Q3: the refill pre-inserted this position (or the next)
         const bool dirty = hashed && (!first_in_slot || hard);
         int best = MIN_MATCH - 1, mstart = 0;
@@ -590,11 +598,12 @@ __device__ void slow_tile_insert(const Smem& sm, int S, int T, int hash_variant)
         const uint32_t key = (seq << 5) | (uint32_t)(31 - lane);
         if (on) {
             h = hash_of(sm, lds_u32_unaligned(sm.win, p + (MIN_MATCH - 1)), hash_variant);
-            atomicMax(&sm.slot[h & SLOT_MASK], key);
+            atomicMax(&sm.slot[h & sm.slot_mask], key);
             c0 = sm.head[h];
         }
         __syncwarp();
-        const bool first = on && sm.slot[h & SLOT_MASK] == key;
+        const bool first = on && sm.slot[h & sm.slot_mask] == key;
+        if (on && sm.shadow) sm.shadow[p & (SHADOW_N - 1)] = sm.prev[p & W_MASK];   // slots of one group of 32 are distinct
         if (first) {   // the only position of its hash so far in this group of 32: InsertString (Deflate.cs:866-877)
             if (c0 != p) {
                 sm.prev[p & W_MASK] = (uint16_t)c0;
@@ -635,6 +644,43 @@ __device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const Le
             const int off = best >= 3 ? best - 3 : 0;
             const uint32_t mask = best >= 3 ? 0xffffffffu : 0x00ffffffu;
             const int nxt = sm.prev[cur & W_MASK];
+            if (((lds_u32_unaligned(sm.win, cur + off) ^ lds_u32_unaligned(sm.win, p + off)) & mask) == 0) {
+                const int L = common_prefix258(sm.win, p, cur);
+                if (L > best) {
+                    best = L;
+                    ms = cur;
+                    if (L >= cfg.nice) break;
+                }
+            }
+            if (j == early_budget) {
+                early = (uint32_t)best | ((uint32_t)ms << 9);
+                have_early = true;
+            }
+            cur = nxt;
+        } while (cur > limit && --chain != 0);
+    }
+    const uint32_t full = (uint32_t)best | ((uint32_t)ms << 9);
+    return make_uint2(full, have_early ? early : full);
+}
+
+// (B) for the wide pipelined tile: slow_tile_search, except that a link whose prev[] slot has meanwhile been reused by a
+// position of the same tile (32768 further on) is read from the shadow copy taken at that insert.
+__device__ uint2 slow_tile_search_sh(const Smem& sm, int p, int hash_head, const LevelCfg& cfg)
+{
+    int best = MIN_MATCH - 1, ms = 0;
+    uint32_t early = 0;
+    bool have_early = false;
+    if (hash_head != 0 && p - hash_head <= MAX_DIST) {
+        const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
+        const int early_budget = cfg.chain >> 2;
+        int chain = cfg.chain, j = 0, cur = hash_head;
+        do {
+            if (cur >= p) break;
+            j++;
+            const int off = best >= 3 ? best - 3 : 0;
+            const uint32_t mask = best >= 3 ? 0xffffffffu : 0x00ffffffu;
+            const int reuse = cur + W_SIZE;
+            const int nxt = (reuse >= sm.shadow_lo && reuse < sm.shadow_hi) ? sm.shadow[reuse & (SHADOW_N - 1)] : sm.prev[cur & W_MASK];
             if (((lds_u32_unaligned(sm.win, cur + off) ^ lds_u32_unaligned(sm.win, p + off)) & mask) == 0) {
                 const int L = common_prefix258(sm.win, p, cur);
                 if (L > best) {
@@ -1095,10 +1141,16 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
     sm.crc = sm.prev + W_SIZE;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm.crc + 1024);
     uint32_t* red = reinterpret_cast<uint32_t*>(bar + 1);  // 2 * 8 * u64
+    constexpr int REC_N = NT == 1024 ? 2 * WIDE_TILE : TILE_MAX;      // 1024-thread kernel: two wide tile buffers
+    constexpr int SLOTS = NT == 1024 ? WIDE_SLOTS : SLOT_COUNT;
     sm.tile_rec = reinterpret_cast<uint2*>(red + 128);
-    sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + 3 * TILE_MAX);   // three tile buffers (pipelined DeflateSlow)
-    sm.tile_hh = reinterpret_cast<uint16_t*>(sm.slot + SLOT_COUNT);
-    sm.fast_masks = reinterpret_cast<uint32_t*>(sm.tile_hh + 3 * TILE_MAX);
+    sm.slot = reinterpret_cast<uint32_t*>(sm.tile_rec + REC_N);
+    sm.slot_mask = SLOTS - 1;
+    sm.tile_hh = reinterpret_cast<uint16_t*>(sm.slot + SLOTS);
+    uint16_t* shadow_buf = sm.tile_hh + REC_N;                         // SHADOW_N entries (1024-thread kernel only)
+    sm.shadow = nullptr;
+    sm.shadow_lo = sm.shadow_hi = 0;
+    sm.fast_masks = reinterpret_cast<uint32_t*>(shadow_buf + (NT == 1024 ? SHADOW_N : 0));
     sm.fast_endl = reinterpret_cast<uint16_t*>(sm.fast_masks + 16);
     sm.fast_mst = sm.fast_endl + 64;
     ParserState* shared_state = reinterpret_cast<ParserState*>(sm.fast_mst + 64);
@@ -1111,7 +1163,7 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 1024; i += LZ_THREADS) sm.crc[i] = P.crc_tab[i];
-    for (int i = tid; i < SLOT_COUNT; i += LZ_THREADS) sm.slot[i] = 0;
+    for (int i = tid; i < SLOTS; i += LZ_THREADS) sm.slot[i] = 0;
     if (tid == 0) *sm.batch_seq = 0;
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -1261,7 +1313,7 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                 // end skipped -- worth more than the overlap when the search dominates (level 9, mixed data: 2.8 s vs 3.3 s
                 // per 256 MiB).
                 // ---- pipelined tiles: warp 0 replays tile k while warps 1..31 insert and search tile k + 1 -----------------
-                constexpr int TP = 248;   // positions per tile: 31 producer warps x 8 quads
+                constexpr int TP = WIDE_TILE;   // positions per tile: one per thread of the 31 producer warps
                 const int S0 = shared_state->str_start;
                 const int avail = shared_state->lookahead - (MIN_LOOKAHEAD - 1);
                 if (tid == 0) { pipe_flags[0] = 0; pipe_flags[1] = 0; }
@@ -1285,8 +1337,8 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                             if (tid == 0) while (pipe_flags[0] < k + 1) __nanosleep(100);   // back off: a spinning warp takes issue slots from the producers
                             __syncwarp();
                             __threadfence_block();
-                            smb.tile_rec = sm.tile_rec + (k % 3) * TILE_MAX;
-                            smb.tile_hh = sm.tile_hh + (k % 3) * TILE_MAX;
+                            smb.tile_rec = sm.tile_rec + (k & 1) * WIDE_TILE;
+                            smb.tile_hh = sm.tile_hh + (k & 1) * WIDE_TILE;
                             if (s.str_start < tS + tT) slow_tile_replay_warp(smb, s, o, cfg, P.strategy, P.hash_variant, tS, tT);
                             __syncwarp();
                             if (tid == 0) {
@@ -1299,16 +1351,18 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                         const int ptid = tid - 32;
                         for (int k = 0; k < ntiles; k++) {
                             const int tS = S0 + k * TP, tT = L - tS < TP ? L - tS : TP;
-                            // Three buffers: tile k reuses the buffer of tile k - 3.  Two would deadlock when a match that starts in
-                            // tile n - 3 runs past the last (short) tile: the replay then waits for every tile (pipe_wait_all) while
-                            // the last tile would wait for the replay to leave tile n - 3.
-                            if (ptid == 0 && k >= 3) while (pipe_flags[1] < k - 2) __nanosleep(100);
+                            // Two buffers: tile k reuses the buffer of tile k - 2.  No deadlock with pipe_wait_all: a match can run
+                            // past L only from the last two tiles (a tile is 992 positions, a match at most 258).
+                            if (ptid == 0 && k >= 2) while (pipe_flags[1] < k - 1) __nanosleep(100);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
-                            smb.tile_rec = sm.tile_rec + (k % 3) * TILE_MAX;
-                            smb.tile_hh = sm.tile_hh + (k % 3) * TILE_MAX;
+                            smb.tile_rec = sm.tile_rec + (k & 1) * WIDE_TILE;
+                            smb.tile_hh = sm.tile_hh + (k & 1) * WIDE_TILE;
+                            smb.shadow = shadow_buf;
+                            smb.shadow_lo = tS;
+                            smb.shadow_hi = tS + tT;
                             if (ptid < 32) slow_tile_insert(smb, tS, tT, P.hash_variant);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
-                            if (ptid < 4 * tT) slow_tile_search_quad(smb, tS, ptid >> 2, cfg);
+                            if (ptid < tT) smb.tile_rec[ptid] = slow_tile_search_sh(smb, tS + ptid, smb.tile_hh[ptid], cfg);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
                             if (ptid == 0) {
                                 __threadfence_block();
@@ -1382,10 +1436,13 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
     }
 }
 
-size_t lz77_smem_bytes()
+size_t lz77_smem_bytes(int threads)
 {
-    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 128 * 4 + sizeof(ParserState) + 16 + SLOT_COUNT * 4 + 16 + 768 * 8 + 768 * 2 + 64 + 128 + 128;
+    const size_t rec_n = threads == 1024 ? 2 * WIDE_TILE : TILE_MAX, slots = threads == 1024 ? WIDE_SLOTS : SLOT_COUNT;
+    return WINDOW_SIZE + WIN_PAD + HASH_SIZE * 2 + W_SIZE * 2 + 1024 * 2 + 8 + 128 * 4 + sizeof(ParserState) + 16 + slots * 4 + 16 +
+           rec_n * 8 + rec_n * 2 + (threads == 1024 ? SHADOW_N * 2 : 0) + 64 + 128 + 128;
 }
+size_t lz77_smem_bytes() { return lz77_smem_bytes(256); }
 
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
 {
@@ -1393,11 +1450,11 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
     static const bool no_symbolize = getenv("ZSB_NO_SYMBOLIZE") != nullptr;
     if (!no_symbolize && !P.stats && symbolize_applies(P)) return launch_symbolize(P, num_sms, stream);
     static bool configured = false;
-    size_t smem = lz77_smem_bytes();
+    const size_t smem = lz77_smem_bytes(256), smem_wide = lz77_smem_bytes(1024);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(lz77_segments_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(lz77_segments_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(lz77_segments_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -1408,7 +1465,7 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
         const char* e = getenv("ZSB_SLOW_THREADS");
         return !(e && atoi(e) == 256);
     }();
-    if (P.fn == FN_SLOW && slow_wide) lz77_segments_kernel<1024, true><<<grid, 1024, smem, stream>>>(P);
+    if (P.fn == FN_SLOW && slow_wide) lz77_segments_kernel<1024, true><<<grid, 1024, smem_wide, stream>>>(P);
     else lz77_segments_kernel<256, false><<<grid, 256, smem, stream>>>(P);
     return cudaGetLastError();
 }

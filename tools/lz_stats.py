@@ -16,8 +16,8 @@ import torch  # noqa: E402
 import synth  # noqa: E402
 from zlibstream_b200 import Engine  # noqa: E402
 
-NAMES = ["batches", "consumed", "dirty_stops", "nact_sum", "cyc_spec_links", "cyc_rounds", "x6", "x7",
-         "matches", "x9", "cyc_fill", "cyc_parse", "x12", "x13", "serial_inserts", "rounds"]
+NAMES = ["batches", "consumed", "dirty_stops", "nact_sum", "cyc_spec_links/insert", "cyc_rounds/search", "cyc_replay", "cyc_prod_wait",
+         "matches/cyc_replay_wait", "x9", "cyc_fill", "cyc_parse", "x12", "x13", "serial_inserts", "rounds"]
 
 
 def main():

@@ -674,19 +674,27 @@ __device__ uint2 slow_tile_search_sh(const Smem& sm, int p, int hash_head, const
         const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
         const int early_budget = cfg.chain >> 2;
         int chain = cfg.chain, j = 0, cur = hash_head;
+        // A candidate can only beat `best` if it agrees with the scan string at [best] and on the bytes up to it: one byte
+        // load rejects most candidates, the scan side of both tests stays in registers until `best` changes.
+        int off = 0;
+        uint32_t mask = 0x00ffffffu;
+        uint32_t scan_w = lds_u32_unaligned(sm.win, p);
+        uint32_t scan_b = sm.win[p + best];
         do {
             if (cur >= p) break;
             j++;
-            const int off = best >= 3 ? best - 3 : 0;
-            const uint32_t mask = best >= 3 ? 0xffffffffu : 0x00ffffffu;
             const int reuse = cur + W_SIZE;
             const int nxt = (reuse >= sm.shadow_lo && reuse < sm.shadow_hi) ? sm.shadow[reuse & (SHADOW_N - 1)] : sm.prev[cur & W_MASK];
-            if (((lds_u32_unaligned(sm.win, cur + off) ^ lds_u32_unaligned(sm.win, p + off)) & mask) == 0) {
+            if (sm.win[cur + best] == scan_b && ((lds_u32_unaligned(sm.win, cur + off) ^ scan_w) & mask) == 0) {
                 const int L = common_prefix258(sm.win, p, cur);
                 if (L > best) {
                     best = L;
                     ms = cur;
                     if (L >= cfg.nice) break;
+                    off = best - 3;
+                    mask = 0xffffffffu;
+                    scan_w = lds_u32_unaligned(sm.win, p + off);
+                    scan_b = sm.win[p + best];
                 }
             }
             if (j == early_budget) {
@@ -1307,11 +1315,11 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                     fast_bar();
                     if (tid == 0) *shared_state = s;
                 }
-            } else if (cfg.fn == FN_SLOW && NT == 1024 && P.strategy != 2 && !P.stats && cfg.chain <= 128) {
-                // Levels 4-6 only: on a fixed tile grid every position below L is searched, whereas the tile-at-a-time loop
-                // below starts each tile where the parse stands and so never searches what a match that crossed the tile
-                // end skipped -- worth more than the overlap when the search dominates (level 9, mixed data: 2.8 s vs 3.3 s
-                // per 256 MiB).
+            } else if (cfg.fn == FN_SLOW && NT == 1024 && P.strategy != 2) {
+                // Every level 4-9 (wide tiles, level 9 mixed data: 2.33 s per 256 MiB against 2.79 s for the tile-at-a-time
+                // loop below with four threads per position).  Tried and backed out: a dedicated insert warp running one
+                // tile ahead of the search (A overlapped with B) -- the insert is a chain of dependent shared-memory round
+                // trips, and under the load of 30 search warps it became the bottleneck (L6 text 91 -> 200 ms per 256 MiB).
                 // ---- pipelined tiles: warp 0 replays tile k while warps 1..31 insert and search tile k + 1 -----------------
                 constexpr int TP = WIDE_TILE;   // positions per tile: one per thread of the 31 producer warps
                 const int S0 = shared_state->str_start;
@@ -1334,8 +1342,10 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                         ParserState s = *shared_state;
                         for (int k = 0; k < ntiles; k++) {
                             const int tS = S0 + k * TP, tT = L - tS < TP ? L - tS : TP;
+                            const long long tw0 = P.stats ? clock64() : 0;
                             if (tid == 0) while (pipe_flags[0] < k + 1) __nanosleep(100);   // back off: a spinning warp takes issue slots from the producers
                             __syncwarp();
+                            const long long tw1 = P.stats ? clock64() : 0;
                             __threadfence_block();
                             smb.tile_rec = sm.tile_rec + (k & 1) * WIDE_TILE;
                             smb.tile_hh = sm.tile_hh + (k & 1) * WIDE_TILE;
@@ -1344,6 +1354,12 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                             if (tid == 0) {
                                 __threadfence_block();
                                 pipe_flags[1] = k + 1;
+                                if (P.stats) {
+                                    atomicAdd(P.stats + 0, 1ull);
+                                    atomicAdd(P.stats + 3, (unsigned long long)tT);
+                                    atomicAdd(P.stats + 8, (unsigned long long)(tw1 - tw0));          // replay waits for a tile
+                                    atomicAdd(P.stats + 6, (unsigned long long)(clock64() - tw1));    // replay
+                                }
                             }
                         }
                         if (tid == 0) *shared_state = s;
@@ -1353,8 +1369,10 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                             const int tS = S0 + k * TP, tT = L - tS < TP ? L - tS : TP;
                             // Two buffers: tile k reuses the buffer of tile k - 2.  No deadlock with pipe_wait_all: a match can run
                             // past L only from the last two tiles (a tile is 992 positions, a match at most 258).
+                            const long long tp0 = P.stats ? clock64() : 0;
                             if (ptid == 0 && k >= 2) while (pipe_flags[1] < k - 1) __nanosleep(100);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
+                            const long long tp1 = P.stats ? clock64() : 0;
                             smb.tile_rec = sm.tile_rec + (k & 1) * WIDE_TILE;
                             smb.tile_hh = sm.tile_hh + (k & 1) * WIDE_TILE;
                             smb.shadow = shadow_buf;
@@ -1362,11 +1380,17 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                             smb.shadow_hi = tS + tT;
                             if (ptid < 32) slow_tile_insert(smb, tS, tT, P.hash_variant);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
+                            const long long tp2 = P.stats ? clock64() : 0;
                             if (ptid < tT) smb.tile_rec[ptid] = slow_tile_search_sh(smb, tS + ptid, smb.tile_hh[ptid], cfg);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
                             if (ptid == 0) {
                                 __threadfence_block();
                                 pipe_flags[0] = k + 1;
+                                if (P.stats) {
+                                    atomicAdd(P.stats + 7, (unsigned long long)(tp1 - tp0));          // producers wait for a buffer
+                                    atomicAdd(P.stats + 4, (unsigned long long)(tp2 - tp1));          // insert
+                                    atomicAdd(P.stats + 5, (unsigned long long)(clock64() - tp2));    // search
+                                }
                             }
                         }
                     }

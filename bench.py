@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=0, help="0 = sized for ~10 s of CPU work")
     ap.add_argument("--no-inflate", action="store_true")
     ap.add_argument("--no-inflate-large", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -305,6 +306,11 @@ def run_ours(args):
                                       "roofline_frac": (n * reps * (1 + ratio) / (bm / 1e3) / 1e9) / _hbm_peak()[0]}
         del big, big_dec, big_ends
 
+    # ---- the other BASELINE.json configurations, 256 MiB each, kernel time (context for the headline; not bench lines) ----
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(eng, data, dev)
+
     # ---- e2e: same call through the C ABI with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -332,6 +338,8 @@ def run_ours(args):
         line["inflate"] = inflate
     if e2e:
         line["e2e"] = e2e
+    if other:
+        line["other_configs"] = other
     if not args.no_cpu:
         cores = os.cpu_count() or 1
         sample_mib = args.cpu_sample_mib or max(64, min(args.size_mib, 16 * cores))
@@ -396,6 +404,54 @@ def _hbm_peak():
         return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     except Exception:
         return 6650.0, "6.65 TB/s (of fallback, B200_PROFILING.md)"
+
+
+def other_configs(eng, text, dev, mib=256):
+    """Deflate + inflate kernel throughput of the remaining BASELINE.json configurations at 256 MiB each (synthetic data of
+    each named shape: tests/corpus_data generators tiled on the device).  Every output is inflated back and compared."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import corpus_data
+    n = mib << 20
+
+    def tile(host_bytes):
+        t = torch.frombuffer(bytearray(host_bytes), dtype=torch.uint8).to(dev)
+        return t.repeat((n + t.numel() - 1) // t.numel())[:n].contiguous()
+
+    def run(name, d, level, strategy, seg):
+        nseg = (d.numel() + seg - 1) // seg
+        cap = eng.deflate_bound(d.numel(), seg)
+        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        ends = torch.empty(nseg, dtype=torch.int64, device=dev)
+        best = None
+        for _ in range(2):
+            clen, _ = eng.deflate_segments_device(d.data_ptr(), d.numel(), seg, level, strategy, HASH, 0, out.data_ptr(), cap,
+                                                  ends.data_ptr(), trailer=False)
+            k = eng.last_kernel_ms()
+            t = k["lz77"] + k["huffman"]
+            best = t if best is None else min(best, t)
+        dec = torch.empty(d.numel(), dtype=torch.uint8, device=dev)
+        ims = None
+        for _ in range(2):
+            eng.inflate_segments_device(out.data_ptr(), clen, ends.data_ptr(), nseg, seg, dec.data_ptr(), d.numel(), header=True,
+                                        trailer=False)
+            t = eng.last_kernel_ms()["inflate"]
+            ims = t if ims is None else min(ims, t)
+        torch.cuda.synchronize()
+        return {"workload": name, "level": level, "strategy": strategy, "segment_bytes": seg, "mib": d.numel() >> 20,
+                "ratio": round(clen / d.numel(), 4), "deflate_gbs": round(d.numel() / best / 1e6, 2),
+                "inflate_gbs": round(d.numel() / ims / 1e6, 2), "round_trip_ok": bool(torch.equal(dec, d))}
+
+    res = [run("text-like", text[:n].contiguous(), 6, 0, 65536)]
+    mixed = tile(corpus_data.mixed_entropy(32 << 20, seed=2))
+    res.append(run("mixed-entropy", mixed, 6, 0, 262144))
+    res.append(run("mixed-entropy", mixed, 9, 0, 262144))
+    del mixed
+    png = tile(corpus_data.png_like(32 << 20, seed=3))
+    res.append(run("png-like Filtered", png, 6, 1, 65536))
+    res.append(run("png-like HuffmanOnly", png, 6, 2, 65536))
+    res.append(run("png-like Rle", png, 6, 3, 65536))
+    return res
 
 
 def _traffic_from_profile(n):

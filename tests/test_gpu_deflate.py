@@ -211,3 +211,19 @@ def test_parallel_symbolizer_rle_and_huffman_only(engine, oracle, ss):
             want, want_ends, want_adler = oracle.deflate_segments(data, ss, level, strategy)
             got, ends, adler = engine.deflate_segments(data, ss, level, strategy)
             assert got == want and ends == want_ends and adler == want_adler, (len(data), level, strategy)
+
+
+@pytest.mark.parametrize("level", [4, 5, 7, 8])
+def test_slow_pipeline_stress(engine, oracle, corpus, level):
+    """Levels 4-9 run as a three-stage pipeline over 992-position tiles with a shadow of reused prev[] slots
+    (zsb_lz77.cu): long runs (matches that skip past tile ends and past the pre-inserted region), incompressible
+    stretches, short last segments, refills in the middle of a tile, 128 KiB and 256 KiB segments."""
+    rng = np.random.RandomState(level)
+    blob = b"".join(corpus[k] for k in sorted(corpus))
+    parts = [blob[:300000], bytes(70000), rng.bytes(50000), b"abcdefgh" * 9000, blob[300000:500000], b"\x01" * 1000,
+             _run_lengths_data(level, 200000), corpus_data.mixed_entropy(400000, seed=level)]
+    data = b"".join(parts)
+    for ss, strategy in ((65536, 0), (131072, 0), (262144, 1)):
+        want, want_ends, want_adler = oracle.deflate_segments(data, ss, level, strategy)
+        got, ends, adler = engine.deflate_segments(data, ss, level, strategy)
+        assert got == want and ends == want_ends and adler == want_adler, (level, ss, strategy)

@@ -78,6 +78,8 @@ struct Lane {
     uint32_t limit;        // bytes that may be loaded (to the end of the whole compressed buffer)
     uint64_t acc;          // bit accumulator, LSB first; bits above nbits are zero
     int nbits;
+    uint32_t pre;          // the input word at `pos`, loaded one refill ahead (the L1 left beside 224 KiB of tables is
+    int pre_ok;            //   too small to keep input lines, so an on-demand word costs an L2 round trip)
     uint8_t* ob8;          // 8-byte aligned base of the output: segment start minus sh
     uint32_t sh;           // misalignment of the segment's first output byte (0 for cudaMalloc'ed buffers)
     uint32_t v;            // sh + bytes produced; wbuf holds the bytes [v & ~7, v)
@@ -194,14 +196,15 @@ ZL_HD void refill(Lane& L)
     if (L.nbits > 32) return;
     const uint8_t* p = L.in + L.pos;
     if (((uintptr_t)p & 3u) == 0 && L.pos + 4 <= L.limit) {
-        L.acc |= (uint64_t)ld_in_u32(p) << L.nbits;
-#ifdef __CUDA_ARCH__
-        if (((uintptr_t)p & 31u) == 0 && L.pos + 128 <= L.limit) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 96));   // the stream is read front to back
-#endif
+        const uint32_t w = L.pre_ok ? L.pre : ld_in_u32(p);
+        L.acc |= (uint64_t)w << L.nbits;
         L.pos += 4;
         L.nbits += 32;
+        L.pre_ok = L.pos + 4 <= L.limit;
+        if (L.pre_ok) L.pre = ld_in_u32(p + 4);   // not needed before the next refill: its latency hides behind ~4 symbols
         return;
     }
+    L.pre_ok = 0;
     // start of a segment, after a stored block, last bytes of the buffer
     while (L.nbits <= 56 && L.pos < L.limit) {
         L.acc |= (uint64_t)ld_in_u8(L.in + L.pos) << L.nbits;
@@ -341,6 +344,7 @@ ZL_HD void block_step(Lane& L)
         if (src + l > L.end) return lane_fail(L, IE_TRUNCATED);
         if (L.v + l > L.vcap) return lane_fail(L, IE_OUTPUT_OVERFLOW);
         L.pos = src;
+        L.pre_ok = 0;
         L.acc = 0;
         L.nbits = 0;
         L.stored_rem = l;
@@ -580,6 +584,8 @@ ZL_HD void begin_segment(Lane& L, const InflateParams& P, uint32_t seg)
     L.err = IE_OK;
     L.st = S_BLOCK;
     L.pos = 0;
+    L.pre = 0;
+    L.pre_ok = 0;
     L.acc = 0;
     L.nbits = 0;
     L.end = 0;

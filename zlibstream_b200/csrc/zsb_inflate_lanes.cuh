@@ -35,7 +35,10 @@ namespace lanes {
 #define ZSB_LN_ROOT_L 8
 #endif
 constexpr int ROOT_L = ZSB_LN_ROOT_L;   // literal/length root table bits
-constexpr int ROOT_D = 6;               // distance root table bits
+#ifndef ZSB_LN_ROOT_D
+#define ZSB_LN_ROOT_D 6
+#endif
+constexpr int ROOT_D = ZSB_LN_ROOT_D;   // distance root table bits
 constexpr int ROOT_BL = 7;              // bit-length code: always complete within the root (MAX_BL_BITS)
 #ifndef ZSB_LN_LONG_L
 #define ZSB_LN_LONG_L 96

@@ -267,28 +267,65 @@ __global__ void __launch_bounds__(SY_THREADS) symbolize_segments_kernel(Lz77Para
 
         // ---- D: write the symbols (Tr_tally_lit / Tr_tally_dist), note where blocks begin and end ----------------------
         uint32_t* sym = P.sym + (size_t)seg * P.sym_stride;
+        const bool sym_aligned = (reinterpret_cast<uintptr_t>(sym) & 15) == 0;
         for (int k = 0; k < K; k++) {
             const int w = tid * K + k, p0 = w * 32;
             uint32_t S = sm.start[w];
             if (!S) continue;
             const uint32_t E = sm.eq[w], Z = ~E;
+            uint32_t idx = sm.base[w];
+            // the word's 32 bytes, once (the per-literal byte loads of the first version went to L2 one at a time)
+            uint32_t x[8];
+            const bool whole = aligned && p0 + 32 <= n;
+            if (whole) {
+                const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(in + p0)), v1 = __ldg(reinterpret_cast<const uint4*>(in + p0 + 16));
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            }
+            if (whole && S == 0xffffffffu && E == 0) {
+                // 32 literals in a row (HuffmanOnly always, Rle on run-free data): records straight from the registers
+                const uint32_t blk0 = idx / BLOCK_SYMS, off0 = idx - blk0 * BLOCK_SYMS;
+                if (off0 == 0 && blk0 < SY_MAX_BLOCKS) blk_first[blk0] = p0;
+                const uint32_t j = BLOCK_SYMS - 1 - off0;   // the record that completes block blk0, if it is one of these
+                if (j < 32) {
+                    if (blk0 < SY_MAX_BLOCKS) blk_last[blk0] = p0 + (int)j;
+                    if (j + 1 < 32 && blk0 + 1 < SY_MAX_BLOCKS) blk_first[blk0 + 1] = p0 + (int)j + 1;
+                }
+                if (sym_aligned && (idx & 3u) == 0) {
+                    uint4* d = reinterpret_cast<uint4*>(sym + idx);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint32_t v = x[q];
+                        d[q] = make_uint4((v & 0xFFu) << 16, (v & 0xFF00u) << 8, v & 0xFF0000u, (v >> 8) & 0xFF0000u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) sym[idx + i] = ((x[i >> 2] >> (8 * (i & 3))) & 0xFFu) << 16;
+                }
+                continue;
+            }
             const int a = w > 0 ? sm.zprev[w - 1] : -1;
             const int e_out = w + 1 < nwords ? min(sm.znext[w + 1], n) : n;
-            uint32_t idx = sm.base[w];
             while (S) {
                 const int i = __ffs(S) - 1;
                 S &= S - 1;
                 const int p = p0 + i;
-                uint32_t rec;
-                if ((Z >> i) & 1u) rec = (uint32_t)__ldg(in + p) << 16;
-                else {
+                int s = 1;
+                if (!((Z >> i) & 1u)) {
                     const uint32_t zb = Z & ((1u << i) - 1u);
                     const int aa = zb ? p0 + 31 - __clz(zb) : a;
                     const uint32_t za = i < 31 ? Z & (0xffffffffu << (i + 1)) : 0;
                     const int ee = za ? min(p0 + __ffs(za) - 1, n) : e_out;
-                    const int s = rle_symbol_at(p, aa, ee);
-                    rec = s >= MIN_MATCH ? 1u | ((uint32_t)(s - MIN_MATCH) << 16) : (uint32_t)__ldg(in + p) << 16;
+                    s = rle_symbol_at(p, aa, ee);
                 }
+                uint32_t rec;
+                if (s >= MIN_MATCH) rec = 1u | ((uint32_t)(s - MIN_MATCH) << 16);
+                else if (whole) {
+                    const int q = i >> 2;   // byte i of the registers, without indexing them dynamically
+                    const uint32_t lo = q & 1 ? ((q & 2) ? ((q & 4) ? x[7] : x[3]) : ((q & 4) ? x[5] : x[1]))
+                                              : ((q & 2) ? ((q & 4) ? x[6] : x[2]) : ((q & 4) ? x[4] : x[0]));
+                    rec = ((lo >> (8 * (i & 3))) & 0xFFu) << 16;
+                } else rec = (uint32_t)__ldg(in + p) << 16;
                 sym[idx] = rec;
                 const uint32_t blk = idx / BLOCK_SYMS, off = idx - blk * BLOCK_SYMS;
                 if (off == 0 && blk < SY_MAX_BLOCKS) blk_first[blk] = p;

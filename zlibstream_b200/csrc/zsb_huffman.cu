@@ -229,7 +229,10 @@ __device__ void send_tree(BitSink& o, const CodeData* tree, int max_code, const 
     }
 }
 
-constexpr int BT_THREADS = 128;
+#ifndef ZSB_BT_THREADS
+#define ZSB_BT_THREADS 128
+#endif
+constexpr int BT_THREADS = ZSB_BT_THREADS;
 
 struct TreesSmem {
     uint32_t lfreq[L_CODES + 2];

@@ -708,95 +708,6 @@ __device__ uint2 slow_tile_search_sh(const Smem& sm, int p, int hash_head, const
     return make_uint2(full, have_early ? early : full);
 }
 
-// (B) with FOUR threads per position (a quad of adjacent lanes), for the 1024-thread kernel.  Longest_match's outcome
-// depends only on the common-prefix lengths L_1, L_2, ... of the candidates in chain order: it is the first candidate with
-// L >= nice_match if there is one within the budget, else the longest one (the earliest among equals); the pre-filters
-// only skip candidates that cannot beat the running best.  So lane q of the quad walks the whole chain (links are one
-// dependent shared-memory load each) but compares only candidates q+1, q+5, q+9, ... against ITS OWN running best (a
-// candidate that cannot beat the lane's best cannot beat the quad's), and the quad merges: minimum step with L >= nice,
-// else maximum L with the smallest step.  One iteration = four chain steps.  The result for the reduced budget
-// (chain >> 2, a multiple of 4 at every level) is the merge after that many steps.
-// Measured (profiles/r01i_config_sweep.jsonl vs r01j): 1.6x faster than one thread per position at level 9, 1.1-1.2x at
-// level 6 on mixed and PNG-like data (long compares split four ways), 0.9x on text-like level 6 (short compares: the
-// replicated chain walk costs more than it saves).  A variant where only lane 0 walks the chain and shuffles the
-// candidates out, with a one-byte pre-filter, was slower everywhere: the phase is bound by issued instructions
-// (~100 per four steps), not by shared-memory wavefronts (13 % of the pipe).
-__device__ void slow_tile_search_quad(const Smem& sm, int S, int idx, const LevelCfg& cfg)
-{
-    const int lane = threadIdx.x & 31, q = lane & 3;
-    const uint32_t qmask = 0xFu << (lane & ~3);
-    const int p = S + idx;
-    const int hash_head = sm.tile_hh[idx];
-    int best = MIN_MATCH - 1, ms = 0, bstep = 0x7fffffff;       // this lane's best candidate and the step it was met at
-    int nice_step = 0x7fffffff;                                 // first step (of this lane) with L >= nice
-    uint32_t early = 0;
-    bool have_early = false;
-    if (hash_head != 0 && p - hash_head <= MAX_DIST) {          // uniform across the quad
-        const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
-        const int early_budget = cfg.chain >> 2;
-        int cur = hash_head, step = 0, chain = cfg.chain;       // `cur` = candidate of step `step + 1`; same in all four lanes
-        bool alive = true;
-        while (alive) {
-            // candidates of steps step+1 .. step+4: lane q takes the (q+1)-th, all lanes end up at the fifth
-            int mine = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (alive) {
-                    if (cur >= p) alive = false;
-                    else {
-                        if (k == q) mine = cur;
-                        const int nxt = sm.prev[cur & W_MASK];
-                        step++;
-                        cur = nxt;
-                        if (!(cur > limit && --chain != 0)) alive = false;   // the walk ends after this candidate
-                    }
-                }
-            }
-            const int my_step = step - ((step - 1) & 3) + q;    // this iteration's candidates are steps base + 1 .. base + 4
-            if (mine) {
-                const int off = best >= 3 ? best - 3 : 0;
-                const uint32_t mask = best >= 3 ? 0xffffffffu : 0x00ffffffu;
-                if (((lds_u32_unaligned(sm.win, mine + off) ^ lds_u32_unaligned(sm.win, p + off)) & mask) == 0) {
-                    const int L = common_prefix258(sm.win, p, mine);
-                    if (L > best) {
-                        best = L;
-                        ms = mine;
-                        bstep = my_step;
-                        if (L >= cfg.nice && nice_step == 0x7fffffff) nice_step = my_step;
-                    }
-                }
-            }
-            // a candidate with L >= nice ends the reference's walk
-            if (__any_sync(qmask, nice_step != 0x7fffffff)) break;
-            if (step == early_budget && alive) {                // snapshot for the reduced budget (no break happened so far)
-                int b = best, st = bstep, m = ms;
-#pragma unroll
-                for (int d = 1; d < 4; d <<= 1) {
-                    const int ob = __shfl_xor_sync(qmask, b, d), ost = __shfl_xor_sync(qmask, st, d), om = __shfl_xor_sync(qmask, m, d);
-                    if (ob > b || (ob == b && ost < st)) { b = ob; st = ost; m = om; }
-                }
-                early = (uint32_t)b | ((uint32_t)(b > MIN_MATCH - 1 ? m : 0) << 9);
-                have_early = true;
-            }
-        }
-    }
-    // merge: the first step with L >= nice wins outright; candidates met after it do not count
-    int ns = nice_step;
-#pragma unroll
-    for (int d = 1; d < 4; d <<= 1) ns = min(ns, __shfl_xor_sync(qmask, ns, d));
-    int b = best, st = bstep, m = ms;
-    if (st > ns) { b = MIN_MATCH - 1; st = 0x7fffffff; m = 0; }   // only possible for a best found in the final iteration
-#pragma unroll
-    for (int d = 1; d < 4; d <<= 1) {
-        const int ob = __shfl_xor_sync(qmask, b, d), ost = __shfl_xor_sync(qmask, st, d), om = __shfl_xor_sync(qmask, m, d);
-        if (ob > b || (ob == b && ost < st)) { b = ob; st = ost; m = om; }
-    }
-    if (q == 0) {
-        const uint32_t full = (uint32_t)b | ((uint32_t)(b > MIN_MATCH - 1 ? m : 0) << 9);
-        sm.tile_rec[idx] = make_uint2(full, have_early ? early : full);
-    }
-}
-
 // Before the replay inserts a position itself (one past the pre-inserted region), every producer tile must be done:
 // InsertString calls have to happen in position order.
 __device__ __forceinline__ void pipe_wait_all(const Smem& sm)
@@ -1135,8 +1046,8 @@ __device__ void adler_chunk(const uint8_t* p, int n, uint32_t* red, uint32_t& a,
 
 }  // namespace
 
-// NT = 256: every parser (DeflateFast needs the registers).  NT = 1024, SLOW_ONLY: levels 4-9, where the tile search runs
-// four threads per position (slow_tile_search_quad) and 32 warps hide the shared-memory latency of the chain walks.
+// NT = 256: every parser (DeflateFast needs the registers).  NT = 1024, SLOW_ONLY: levels 4-9 as a pipeline over wide
+// tiles (insert / search / replay on different warps, one searched position per producer thread).
 template <int NT, bool SLOW_ONLY>
 __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
 {
@@ -1316,10 +1227,10 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                     if (tid == 0) *shared_state = s;
                 }
             } else if (cfg.fn == FN_SLOW && NT == 1024 && P.strategy != 2) {
-                // Every level 4-9 (wide tiles, level 9 mixed data: 2.33 s per 256 MiB against 2.79 s for the tile-at-a-time
-                // loop below with four threads per position).  Tried and backed out: a dedicated insert warp running one
-                // tile ahead of the search (A overlapped with B) -- the insert is a chain of dependent shared-memory round
-                // trips, and under the load of 30 search warps it became the bottleneck (L6 text 91 -> 200 ms per 256 MiB).
+                // Every level 4-9.  Variants that were measured and dropped (profiles/r01j_slow_pipeline_stats.txt): four threads
+                // per position with a quad merge (more instructions than it saves on short compares), a dedicated insert warp
+                // running one tile ahead of the search (the insert is a chain of dependent shared-memory round trips and
+                // crawls under the load of 30 search warps: L6 text 91 -> 200 ms per 256 MiB).
                 // ---- pipelined tiles: warp 0 replays tile k while warps 1..31 insert and search tile k + 1 -----------------
                 constexpr int TP = WIDE_TILE;   // positions per tile: one per thread of the 31 producer warps
                 const int S0 = shared_state->str_start;
@@ -1417,9 +1328,7 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                     }
                     const long long tB = P.stats ? clock64() : 0;
                     if (P.strategy != 2) {
-                        if (NT >= 4 * TILE_MAX) {
-                            if (tid < 4 * T) slow_tile_search_quad(sm, S, tid >> 2, cfg);
-                        } else if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
+                        if (tid < T) sm.tile_rec[tid] = slow_tile_search(sm, S + tid, sm.tile_hh[tid], cfg);
                         __syncthreads();
                     }
                     const long long tC = P.stats ? clock64() : 0;

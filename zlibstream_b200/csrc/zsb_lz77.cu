@@ -603,7 +603,6 @@ __device__ void slow_tile_insert(const Smem& sm, int S, int T, int hash_variant)
         }
         __syncwarp();
         const bool first = on && sm.slot[h & sm.slot_mask] == key;
-        if (on && sm.shadow) sm.shadow[p & (SHADOW_N - 1)] = sm.prev[p & W_MASK];   // slots of one group of 32 are distinct
         if (first) {   // the only position of its hash so far in this group of 32: InsertString (Deflate.cs:866-877)
             if (c0 != p) {
                 sm.prev[p & W_MASK] = (uint16_t)c0;
@@ -661,6 +660,63 @@ __device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const Le
     }
     const uint32_t full = (uint32_t)best | ((uint32_t)ms << 9);
     return make_uint2(full, have_early ? early : full);
+}
+
+// (A) for the wide pipelined tile, by all 992 producer threads.  InsertString in position order means: position p gets
+// (as return value and as prev link) the nearest earlier position of the tile with the same hash, or the head as it stood
+// before the tile if there is none, and head[h] ends up at the tile's last position with hash h.  So: sort
+// (hash << 10 | index) in shared memory (bitonic, 1024 keys; the tile_rec buffer of this tile is still free), then every
+// position finds its predecessor next to it.  Q2 is kept (no prev write when the value found is the position itself, which
+// happens for the position a refill pre-inserted, Q3), and the old content of every prev slot goes to the shadow first.
+__device__ void slow_tile_insert_sorted(const Smem& sm, int S, int T, int hash_variant, int ptid)
+{
+    uint32_t* keys = reinterpret_cast<uint32_t*>(sm.tile_rec);   // 1024 x u32 <= WIDE_TILE x 8 bytes
+    for (int t = ptid; t < 1024; t += WIDE_TILE) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (t < T) key = (hash_of(sm, lds_u32_unaligned(sm.win, S + t + (MIN_MATCH - 1)), hash_variant) << 10) | (uint32_t)t;
+        keys[t] = key;
+    }
+    asm volatile("bar.sync 3, 992;" ::: "memory");
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = ptid; t < 1024; t += WIDE_TILE) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const uint32_t a = keys[t], b = keys[u];
+                    if ((a > b) == ((t & k) == 0)) {
+                        keys[t] = b;
+                        keys[u] = a;
+                    }
+                }
+            }
+            asm volatile("bar.sync 3, 992;" ::: "memory");
+        }
+    }
+    // predecessor of every position; all reads of the old head before any write
+    int my_p[2] = {0, 0}, my_pred[2] = {0, 0}, my_h[2] = {0, 0};
+    bool my_last[2] = {false, false}, my_on[2] = {false, false};
+    int n = 0;
+    for (int t = ptid; t < 1024; t += WIDE_TILE, n++) {
+        const uint32_t key = keys[t];
+        if (key == 0xFFFFFFFFu) continue;
+        const int h = (int)(key >> 10), i = (int)(key & 1023u);
+        const uint32_t before = t > 0 ? keys[t - 1] : 0xFFFFFFFFu, after = t + 1 < 1024 ? keys[t + 1] : 0xFFFFFFFFu;
+        my_on[n] = true;
+        my_h[n] = h;
+        my_p[n] = S + i;
+        my_pred[n] = (before != 0xFFFFFFFFu && (int)(before >> 10) == h) ? S + (int)(before & 1023u) : (int)sm.head[h];
+        my_last[n] = after == 0xFFFFFFFFu || (int)(after >> 10) != h;
+    }
+    asm volatile("bar.sync 3, 992;" ::: "memory");
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        if (!my_on[m]) continue;
+        const int p = my_p[m], pred = my_pred[m];
+        sm.tile_hh[p - S] = (uint16_t)pred;
+        if (sm.shadow) sm.shadow[p & (SHADOW_N - 1)] = sm.prev[p & W_MASK];
+        if (pred != p) sm.prev[p & W_MASK] = (uint16_t)pred;
+        if (my_last[m]) sm.head[my_h[m]] = (uint16_t)p;
+    }
 }
 
 // (B) for the wide pipelined tile: slow_tile_search, except that a link whose prev[] slot has meanwhile been reused by a
@@ -1289,7 +1345,7 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                             smb.shadow = shadow_buf;
                             smb.shadow_lo = tS;
                             smb.shadow_hi = tS + tT;
-                            if (ptid < 32) slow_tile_insert(smb, tS, tT, P.hash_variant);
+                            slow_tile_insert_sorted(smb, tS, tT, P.hash_variant, ptid);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
                             const long long tp2 = P.stats ? clock64() : 0;
                             if (ptid < tT) smb.tile_rec[ptid] = slow_tile_search_sh(smb, tS + ptid, smb.tile_hh[ptid], cfg);

@@ -728,37 +728,46 @@ __device__ uint2 slow_tile_search_sh(const Smem& sm, int p, int hash_head, const
     bool have_early = false;
     if (hash_head != 0 && p - hash_head <= MAX_DIST) {
         const int limit = p > MAX_DIST ? p - MAX_DIST : 0;
-        const int early_budget = cfg.chain >> 2;
-        int chain = cfg.chain, j = 0, cur = hash_head;
+        int cur = hash_head;
         // A candidate can only beat `best` if it agrees with the scan string at [best] and on the bytes up to it: one byte
         // load rejects most candidates, the scan side of both tests stays in registers until `best` changes.
         int off = 0;
         uint32_t mask = 0x00ffffffu;
         uint32_t scan_w = lds_u32_unaligned(sm.win, p);
         uint32_t scan_b = sm.win[p + best];
-        do {
-            if (cur >= p) break;
-            j++;
-            const int reuse = cur + W_SIZE;
-            const int nxt = (reuse >= sm.shadow_lo && reuse < sm.shadow_hi) ? sm.shadow[reuse & (SHADOW_N - 1)] : sm.prev[cur & W_MASK];
-            if (sm.win[cur + best] == scan_b && ((lds_u32_unaligned(sm.win, cur + off) ^ scan_w) & mask) == 0) {
-                const int L = common_prefix258(sm.win, p, cur);
-                if (L > best) {
-                    best = L;
-                    ms = cur;
-                    if (L >= cfg.nice) break;
-                    off = best - 3;
-                    mask = 0xffffffffu;
-                    scan_w = lds_u32_unaligned(sm.win, p + off);
-                    scan_b = sm.win[p + best];
+        const uint32_t sh_lo = (uint32_t)sm.shadow_lo, sh_n = (uint32_t)(sm.shadow_hi - sm.shadow_lo);
+        // Two passes over the same loop body: the first chain >> 2 steps (after which the result for the reduced budget
+        // is noted), then the rest -- the step counter of Longest_match's `chain_length` is the loop bound itself.
+        bool stop = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && !stop; pass++) {
+            int steps = pass == 0 ? (cfg.chain >> 2) : cfg.chain - (cfg.chain >> 2);
+            for (;;) {
+                if (cur >= p) { stop = true; break; }
+                int nxt = sm.prev[cur & W_MASK];
+                if ((uint32_t)(cur + W_SIZE) - sh_lo < sh_n) nxt = sm.shadow[(cur + W_SIZE) & (SHADOW_N - 1)];   // slot reused inside this tile
+                if (sm.win[cur + best] == scan_b && ((lds_u32_unaligned(sm.win, cur + off) ^ scan_w) & mask) == 0) {
+                    const int L = common_prefix258(sm.win, p, cur);
+                    if (L > best) {
+                        best = L;
+                        ms = cur;
+                        if (L >= cfg.nice) { stop = true; break; }
+                        off = best - 3;
+                        mask = 0xffffffffu;
+                        scan_w = lds_u32_unaligned(sm.win, p + off);
+                        scan_b = sm.win[p + best];
+                    }
                 }
+                cur = nxt;
+                --steps;
+                if (!(cur > limit)) { stop = true; if (steps == 0 && pass == 0) { early = (uint32_t)best | ((uint32_t)ms << 9); have_early = true; } break; }
+                if (steps == 0) break;
             }
-            if (j == early_budget) {
+            if (pass == 0 && !stop) {
                 early = (uint32_t)best | ((uint32_t)ms << 9);
                 have_early = true;
             }
-            cur = nxt;
-        } while (cur > limit && --chain != 0);
+        }
     }
     const uint32_t full = (uint32_t)best | ((uint32_t)ms << 9);
     return make_uint2(full, have_early ? early : full);

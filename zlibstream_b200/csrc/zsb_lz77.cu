@@ -671,27 +671,41 @@ __device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const Le
 __device__ void slow_tile_insert_sorted(const Smem& sm, int S, int T, int hash_variant, int ptid)
 {
     uint32_t* keys = reinterpret_cast<uint32_t*>(sm.tile_rec);   // 1024 x u32 <= WIDE_TILE x 8 bytes
-    for (int t = ptid; t < 1024; t += WIDE_TILE) {
-        uint32_t key = 0xFFFFFFFFu;
-        if (t < T) key = (hash_of(sm, lds_u32_unaligned(sm.win, S + t + (MIN_MATCH - 1)), hash_variant) << 10) | (uint32_t)t;
-        keys[t] = key;
-    }
-    asm volatile("bar.sync 3, 992;" ::: "memory");
-    for (int k = 2; k <= 1024; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = ptid; t < 1024; t += WIDE_TILE) {
-                const int u = t ^ j;
-                if (u > t) {
-                    const uint32_t a = keys[t], b = keys[u];
-                    if ((a > b) == ((t & k) == 0)) {
-                        keys[t] = b;
-                        keys[u] = a;
-                    }
+    // Bitonic sort of 1024 keys by the first 512 producer threads, two adjacent keys (2t, 2t + 1) per thread: partners at
+    // distance 1 sit in the same thread, at distance 2..32 one shuffle away, only distance >= 64 goes through shared
+    // memory (10 of the 55 stages).  The other producer threads wait at the barrier below.
+    if (ptid < 512) {
+        const int e0 = 2 * ptid;
+        uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+        if (e0 < T) k0 = (hash_of(sm, lds_u32_unaligned(sm.win, S + e0 + (MIN_MATCH - 1)), hash_variant) << 10) | (uint32_t)e0;
+        if (e0 + 1 < T) k1 = (hash_of(sm, lds_u32_unaligned(sm.win, S + e0 + 1 + (MIN_MATCH - 1)), hash_variant) << 10) | (uint32_t)(e0 + 1);
+        for (int k = 2; k <= 1024; k <<= 1) {
+            const bool up = (e0 & k) == 0;                       // both keys of a thread lie in the same k-block (k >= 2)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j == 1) {
+                    if ((k0 > k1) == up) { const uint32_t x = k0; k0 = k1; k1 = x; }
+                } else if (j <= 32) {
+                    const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, j >> 1), o1 = __shfl_xor_sync(0xffffffffu, k1, j >> 1);
+                    const bool low = (e0 & j) == 0;              // this thread holds the lower element of each pair
+                    // the lower element keeps the minimum in an ascending block, the maximum in a descending one
+                    k0 = (low == up) ? min(k0, o0) : max(k0, o0);
+                    k1 = (low == up) ? min(k1, o1) : max(k1, o1);
+                } else {
+                    keys[e0] = k0;
+                    keys[e0 + 1] = k1;
+                    asm volatile("bar.sync 4, 512;" ::: "memory");
+                    const uint32_t o0 = keys[e0 ^ j], o1 = keys[(e0 + 1) ^ j];
+                    asm volatile("bar.sync 4, 512;" ::: "memory");
+                    const bool low = (e0 & j) == 0;
+                    k0 = (low == up) ? min(k0, o0) : max(k0, o0);
+                    k1 = (low == up) ? min(k1, o1) : max(k1, o1);
                 }
             }
-            asm volatile("bar.sync 3, 992;" ::: "memory");
         }
+        keys[e0] = k0;
+        keys[e0 + 1] = k1;
     }
+    asm volatile("bar.sync 3, 992;" ::: "memory");
     // predecessor of every position; all reads of the old head before any write
     int my_p[2] = {0, 0}, my_pred[2] = {0, 0}, my_h[2] = {0, 0};
     bool my_last[2] = {false, false}, my_on[2] = {false, false};

@@ -100,7 +100,8 @@ ZSB_API size_t zsb_deflate_bound(size_t n, size_t seg_size);
  *                       at window index 0 and has the header counted in the 512-byte chunk arithmetic (Q6, Q10)
  *   halo                with first_segment_index > 0: the 32768 bytes that precede `in` in the stream (same
  *                       memory space as `in`), or NULL; only Rle (Q14) and a short last segment read it
- *   out, out_cap        receives [header] segments... [03 00 adler32]
+ *   out, out_cap        receives [header] segments... [03 00 adler32]; a DEVICE out pointer must be 4-byte aligned
+ *                       (ZSB_STREAM_ERROR otherwise); input pointers and inflate's pointers may have any alignment
  *   out_len             bytes written
  *   seg_end_offsets     optional, one per segment: offset in `out` of the end of the segment
  *                       (== ZlibOutputStream.TotalOut after that Write, minus the bytes this call did not emit)

@@ -227,3 +227,49 @@ def test_slow_pipeline_stress(engine, oracle, corpus, level):
         want, want_ends, want_adler = oracle.deflate_segments(data, ss, level, strategy)
         got, ends, adler = engine.deflate_segments(data, ss, level, strategy)
         assert got == want and ends == want_ends and adler == want_adler, (level, ss, strategy)
+
+
+def test_small_scratch_batches(engine, oracle, monkeypatch):
+    """ZSB_SCRATCH_BYTES bounds the symbol scratch, so a large input goes through the kernels in several batches of
+    segments: batch boundaries must not show (running output offsets, Adler fold, the byte before a batch for Rle / Q14,
+    the previous window for a short last segment / Q7)."""
+    monkeypatch.setenv("ZSB_SCRATCH_BYTES", str(3 * (65536 * 4 + 40000)))   # about three 64 KiB segments per batch
+    data = _run_lengths_data(9, 8 * 65536) + b"\x05" * 70000 + corpus_data.text_like(3 * 65536 + 1234, seed=3)
+    for level, strategy in ((6, 3), (1, 0), (6, 0), (6, 2), (9, 1)):
+        want, want_ends, want_adler = oracle.deflate_segments(data, 65536, level, strategy)
+        got, ends, adler = engine.deflate_segments(data, 65536, level, strategy)
+        assert got == want and ends == want_ends and adler == want_adler, (level, strategy)
+
+
+def test_unaligned_device_pointers(engine, oracle):
+    """Device-pointer entry points with the input at an odd address and the output 4-byte (not 16-byte) aligned (the
+    kernels' aligned fast paths must fall back): deflate of every parser family, then both inflate kernels into an
+    odd-address output.  A device output pointer that is not 4-byte aligned is refused."""
+    import torch
+    data = _run_lengths_data(4, 2 * 65536) + corpus_data.text_like(3 * 65536 + 777, seed=8)
+    n, seg = len(data), 65536
+    nseg = (n + seg - 1) // seg
+    buf = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    buf[3:3 + n] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    cap = engine.deflate_bound(n, seg)
+    out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+    ends = torch.zeros(nseg, dtype=torch.int64, device="cuda")
+    dec = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    for level, strategy in ((1, 0), (6, 0), (6, 2), (6, 3)):
+        want, want_ends, _ = oracle.deflate_segments(data, seg, level, strategy)
+        clen, _ = engine.deflate_segments_device(buf.data_ptr() + 3, n, seg, level, strategy, 0, 0, out.data_ptr() + 4, cap,
+                                                 ends.data_ptr())
+        assert bytes(out[4:4 + clen].cpu().numpy()) == want and ends.cpu().tolist() == want_ends, (level, strategy)
+        for kernel in ("warp", "lanes"):
+            import os
+            os.environ["ZSB_INFLATE_KERNEL"] = kernel
+            try:
+                dec.zero_()
+                got_n, _ = engine.inflate_segments_device(out.data_ptr() + 4, clen, ends.data_ptr(), nseg, seg,
+                                                          dec.data_ptr() + 1, n)
+            finally:
+                del os.environ["ZSB_INFLATE_KERNEL"]
+            assert got_n == n and bytes(dec[1:1 + n].cpu().numpy()) == data, (level, strategy, kernel)
+    from zlibstream_b200 import ZlibStreamException
+    with pytest.raises(ZlibStreamException, match="4-byte aligned"):
+        engine.deflate_segments_device(buf.data_ptr() + 3, n, seg, 1, 0, 0, 0, out.data_ptr() + 5, cap, ends.data_ptr())

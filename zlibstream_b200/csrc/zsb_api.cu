@@ -382,6 +382,9 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     cudaStream_t st = ctx->stream;
     timing_begin(ctx);
 
+    // the bit packer stores 32-bit words relative to `out`; host buffers are staged into an aligned device buffer anyway
+    if ((flags & ZSB_OUT_DEVICE) && (reinterpret_cast<uintptr_t>(out) & 3u)) return fail(ctx, ZSB_STREAM_ERROR, "device output pointer must be 4-byte aligned");
+    if ((flags & ZSB_OFFSETS_DEVICE) && (reinterpret_cast<uintptr_t>(seg_end_offsets) & 7u)) return fail(ctx, ZSB_STREAM_ERROR, "device offsets pointer must be 8-byte aligned");
     const bool write_header = !(flags & ZSB_NO_HEADER);
     const bool write_trailer = !(flags & ZSB_NO_TRAILER);
     const size_t nseg = (n + seg_size - 1) / seg_size;
@@ -457,7 +460,9 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         L.seg_size = (uint32_t)seg_size;
         L.nseg = cnt;
         L.first_seg_index = first_segment_index + s0;
-        L.halo = s0 == 0 ? d_halo : nullptr;
+        // the 32768 bytes before the batch's first segment: the caller's halo for the first batch, the input itself afterwards
+        // (Rle looks one byte back, Q14; a short last segment sees the previous window, Q7)
+        L.halo = s0 == 0 ? d_halo : d_in + s0 * seg_size - W_SIZE;
         L.strategy = strategy;
         L.hash_variant = hash_variant;
         L.good = cfg.good; L.lazy = cfg.lazy; L.nice = cfg.nice; L.chain = cfg.chain;

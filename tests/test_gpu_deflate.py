@@ -273,3 +273,26 @@ def test_unaligned_device_pointers(engine, oracle):
     from zlibstream_b200 import ZlibStreamException
     with pytest.raises(ZlibStreamException, match="4-byte aligned"):
         engine.deflate_segments_device(buf.data_ptr() + 3, n, seg, 1, 0, 0, 0, out.data_ptr() + 5, cap, ends.data_ptr())
+
+
+def test_piped_host_path_equals_device_path(engine, corpus):
+    """With host buffers and enough segments, zsb_deflate_segments uploads / compresses / downloads in overlapping
+    batches.  Its output must be byte for byte what the single-batch device-pointer path produces (which the other tests
+    pin to the oracle), for a parser with a window history (level 1), for Rle (Q14 across batches) and a short last segment."""
+    import torch
+    blob = b"".join(corpus[k] for k in sorted(corpus))
+    seg = 65536
+    data = (blob * (170 * (1 << 20) // len(blob) + 1))[:2500 * seg + 12345]
+    n = len(data)
+    nseg = (n + seg - 1) // seg
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    cap = engine.deflate_bound(n, seg)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_ends = torch.empty(nseg, dtype=torch.int64, device="cuda")
+    for level, strategy in ((1, 0), (6, 3)):
+        clen, d_adler = engine.deflate_segments_device(d_in.data_ptr(), n, seg, level, strategy, 0, 0, d_out.data_ptr(), cap,
+                                                       d_ends.data_ptr())
+        want = bytes(d_out[:clen].cpu().numpy())
+        got, ends, adler = engine.deflate_segments(data, seg, level, strategy)
+        assert len(got) == len(want) and got == want, (level, strategy)
+        assert ends == d_ends.cpu().tolist() and adler == d_adler == zlib.adler32(data)

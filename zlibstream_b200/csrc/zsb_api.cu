@@ -70,6 +70,10 @@ struct zsb_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // host <-> device copies of one batch overlap the kernels of its neighbours
+    static constexpr int kMaxPipe = 8;
+    cudaEvent_t ev_in[kMaxPipe] = {}, ev_done[kMaxPipe] = {};
+    uint64_t* h_totals = nullptr;           // pinned: output offset after each batch
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
@@ -298,6 +302,11 @@ int zsb_ctx_create(int device, zsb_ctx** out)
     if (prop.major < 10) { delete ctx; return ZSB_VERSION_ERROR; }  // built for sm_100a only
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ZSB_ERRNO; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { zsb_ctx_destroy(ctx); return ZSB_ERRNO; }
+    for (int i = 0; i < zsb_ctx::kMaxPipe; i++)
+        if (cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) != cudaSuccess) { zsb_ctx_destroy(ctx); return ZSB_ERRNO; }
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_totals), zsb_ctx::kMaxPipe * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) { zsb_ctx_destroy(ctx); return ZSB_ERRNO; }
     ctx->stream = ctx->own_stream;
     uint16_t tab[1024];
     crc32c_slices(tab);
@@ -327,6 +336,12 @@ void zsb_ctx_destroy(zsb_ctx* ctx)
     if (ctx->crc_tab) cudaFree(ctx->crc_tab);
     if (ctx->lz_stats) cudaFree(ctx->lz_stats);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < zsb_ctx::kMaxPipe; i++) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     delete ctx;
 }
 
@@ -394,9 +409,9 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     const uint8_t* d_in = reinterpret_cast<const uint8_t*>(in);
     if (!(flags & ZSB_IN_DEVICE) && n) {
         CU(ctx->in_stage.reserve(n));
-        CU(cudaMemcpyAsync(ctx->in_stage.p, in, n, cudaMemcpyHostToDevice, st));
-        d_in = ctx->in_stage.as<uint8_t>();
+        d_in = ctx->in_stage.as<uint8_t>();   // filled batch by batch below
     }
+    const bool host_in = !(flags & ZSB_IN_DEVICE) && n, host_out = !(flags & ZSB_OUT_DEVICE);
     const uint8_t* d_halo = reinterpret_cast<const uint8_t*>(halo);
     if (halo && !(flags & ZSB_IN_DEVICE)) {
         CU(ctx->halo_stage.reserve(W_SIZE));
@@ -443,6 +458,27 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     size_t batch = budget / per_seg;
     if (batch < 1) batch = 1;
     if (batch > nseg) batch = nseg;
+    // Host buffers: a few batches, so that the upload of batch b + 1 and the download of batch b - 1's output run beside the
+    // kernels of batch b.  Batches are whole multiples of the SM count (the LZ77 kernels hand out one segment per SM at a time).
+    bool piped = false;
+    if ((host_in || host_out) && nseg >= (size_t)ctx->num_sms * 16) {
+        size_t pb = (nseg + 3) / 4;
+        pb = (pb + ctx->num_sms - 1) / ctx->num_sms * ctx->num_sms;
+        if (pb < batch) batch = pb;
+        piped = (nseg + batch - 1) / batch <= (size_t)zsb_ctx::kMaxPipe;
+    }
+    if (host_in) {
+        if (piped) {
+            int b = 0;
+            for (size_t s0 = 0; s0 < nseg; s0 += batch, b++) {
+                const size_t off = s0 * seg_size, len = std::min(n - off, batch * seg_size);
+                CU(cudaMemcpyAsync(ctx->in_stage.as<uint8_t>() + off, reinterpret_cast<const uint8_t*>(in) + off, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CU(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+            }
+        } else CU(cudaMemcpyAsync(ctx->in_stage.p, in, n, cudaMemcpyHostToDevice, st));
+    }
+    const uint64_t hdr_bytes = write_header ? 2u : 0u;
+    uint64_t copied_to = hdr_bytes;   // host output bytes [hdr_bytes, copied_to) are already on their way
     if (nseg) {
         CU(ctx->sym.reserve(batch * sym_bytes_per_seg));
         CU(ctx->blocks.reserve(batch * max_blocks * sizeof(BlockRec)));
@@ -452,8 +488,10 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     }
 
     const LevelCfg cfg = kLevels[level];
-    for (size_t s0 = 0; s0 < nseg; s0 += batch) {
+    int bidx = 0;
+    for (size_t s0 = 0; s0 < nseg; s0 += batch, bidx++) {
         const uint32_t cnt = (uint32_t)((nseg - s0) < batch ? (nseg - s0) : batch);
+        if (piped && host_in) CU(cudaStreamWaitEvent(st, ctx->ev_in[bidx], 0));
         Lz77Params L;
         L.in = d_in + s0 * seg_size;
         L.n = n - s0 * seg_size;
@@ -508,6 +546,20 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         CU(launch_pack(H, st));
         timing_mark(ctx, 1, false);
         ctx->launches += 3;
+        if (piped && host_out) {
+            // the output of batch b is final once it is packed (segments are byte aligned; only the 2-byte header and the
+            // trailer are written later): note where it ends, and send the previous batch's bytes to the host meanwhile
+            CU(cudaMemcpyAsync(ctx->h_totals + bidx, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(ctx->ev_done[bidx], st));
+            if (bidx > 0) {
+                CU(cudaEventSynchronize(ctx->ev_done[bidx - 1]));
+                const uint64_t upto = std::min<uint64_t>(ctx->h_totals[bidx - 1], out_cap);
+                if (upto > copied_to) {
+                    CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + copied_to, d_out + copied_to, upto - copied_to, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    copied_to = upto;
+                }
+            }
+        }
     }
     // ---- Adler-32 of the whole input, header, trailer ----
     CU(launch_adler_fold(ctx->seg_adler.as<uint2>(), (uint32_t)nseg, (uint32_t)seg_size, n, 1u, d_adler, st));
@@ -526,10 +578,18 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     struct { uint64_t total; int status; uint32_t adler; } fin;
     CU(cudaMemcpyAsync(&fin, small, sizeof fin, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (piped) CU(cudaStreamSynchronize(ctx->copy_stream));   // nothing of this call may still be writing into `out` when it returns
     if (out_len) *out_len = (size_t)fin.total;
     if (adler) *adler = fin.adler;
     if (fin.status != 0 || fin.total > out_cap) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
-    if (!(flags & ZSB_OUT_DEVICE) && fin.total) CU(cudaMemcpyAsync(out, d_out, fin.total, cudaMemcpyDeviceToHost, st));
+    if (host_out && fin.total) {
+        if (piped && copied_to > hdr_bytes && copied_to <= fin.total) {   // header, then what the batches have not sent yet
+            if (hdr_bytes) CU(cudaMemcpyAsync(out, d_out, hdr_bytes, cudaMemcpyDeviceToHost, st));
+            if (fin.total > copied_to)
+                CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + copied_to, d_out + copied_to, fin.total - copied_to, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(ctx->copy_stream));
+        } else CU(cudaMemcpyAsync(out, d_out, fin.total, cudaMemcpyDeviceToHost, st));
+    }
     if (seg_end_offsets && nseg && !(flags & ZSB_OFFSETS_DEVICE))
         CU(cudaMemcpyAsync(seg_end_offsets, d_seg_end, nseg * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -88,6 +88,7 @@ struct Lane {
     uint32_t v;            // sh + bytes produced; wbuf holds the bytes [v & ~7, v)
     uint32_t vcap;         // sh + room
     uint64_t wbuf;
+    uint64_t wprev;        // the word completed last: with wbuf, the most recent 8..15 output bytes without a memory access
     int st, err;
     uint32_t seg;
     int nl, nd, ci, prevlen, fixed;
@@ -239,6 +240,7 @@ ZL_HD void append_byte(Lane& L, uint32_t b)
     L.v++;
     if (a == 7) {
         store_word(L, L.v - 8, L.wbuf);
+        L.wprev = L.wbuf;
         L.wbuf = 0;
     }
 }
@@ -249,6 +251,7 @@ ZL_HD void append_chunk(Lane& L, uint64_t val, uint32_t n)
     L.wbuf |= val << (8 * a);
     if (a + n >= 8) {
         store_word(L, L.v & ~7u, L.wbuf);
+        L.wprev = L.wbuf;
         L.wbuf = a ? val >> (8 * (8 - a)) : 0;
     }
     L.v += n;
@@ -285,10 +288,10 @@ ZL_HD void pattern_setup(Lane& L, uint32_t d)
     L.ph = 0;
     L.pd = d;
     if (L.count) return;
-    flush_partial(L);
-    const uint32_t s = L.v - d, q = s & ~7u, b = s & 7u;
-    uint64_t lo = ld_out_u64(L.ob8 + q) >> (8 * b);
-    if (b + d > 8) lo |= ld_out_u64(L.ob8 + q + 8) << (8 * (8 - b));
+    // the last d <= 8 bytes are in registers: `a` bytes in the word under assembly, the eight before them in wprev
+    // (a distance never reaches before the segment, so what is needed of wprev has been written)
+    const uint32_t a = L.v & 7u, sft = 8u + a - d;   // bytes to drop from the 8 + a recent ones
+    uint64_t lo = sft < 8 ? (L.wprev >> (8 * sft)) | (sft ? L.wbuf << (8 * (8 - sft)) : 0) : L.wbuf >> (8 * (sft - 8));
     if (d < 8) lo &= (1ull << (8 * d)) - 1ull;
     uint64_t hi = 0;
     for (uint32_t f = d; f < 16; f *= 2) {   // (lo, hi) |= (lo, hi) << 8f
@@ -541,6 +544,22 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
         if (pn < 8) val &= (1ull << (8 * pn)) - 1ull;
         append_chunk(L, val, pn);
         L.cp_rem -= pn;
+        // a run needs no loads: up to three more units of it in the same iteration (a 258-byte run in 9 steps, not 33)
+        if (kind == U_PAT || kind == U_ZERO) {
+#pragma unroll 1
+            for (int x = 0; x < 3 && L.cp_rem >= 16; x++) {
+                uint64_t v2 = 0;
+                if (kind == U_PAT) {
+                    const uint32_t ph = L.ph;
+                    v2 = ph ? (L.plo >> (8 * ph)) | (L.phi << (8 * (8 - ph))) : L.plo;
+                    uint32_t nx = ph + (8u % L.pd);
+                    if (nx >= L.pd) nx -= L.pd;
+                    L.ph = nx;
+                }
+                append_chunk(L, v2, 8);
+                L.cp_rem -= 8;
+            }
+        }
     }
     // (d)
     if (!dec) {
@@ -594,6 +613,7 @@ ZL_HD void begin_segment(Lane& L, const InflateParams& P, uint32_t seg)
     L.end = 0;
     L.limit = 0;
     L.wbuf = 0;
+    L.wprev = 0;
     L.fixed = 0;
     L.nl = L.nd = L.ci = L.prevlen = 0;
     L.stored_rem = 0;

@@ -671,14 +671,14 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
     unsigned int* d_carry_flag = reinterpret_cast<unsigned int*>(small + 20);
     CU(cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned int), st));
-    // Two kernels (profiles/r01i_inflate_sweep.txt): a warp per segment decodes one segment fastest and wins while the
+    // Two kernels (profiles/r01i_inflate_sweep.txt, r01n_inflate_sweep.txt): a warp per segment decodes one segment fastest and wins while the
     // segments are few; a lane per segment shares every issued instruction 32 ways and wins once there are enough
     // segments to fill the SMs' resident warps.  ZSB_INFLATE_KERNEL=warp|lanes forces one of them.
     const int forced_kernel = [] {   // read per call: the tests switch kernels at run time
         const char* e = getenv("ZSB_INFLATE_KERNEL");
         return !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : 0;
     }();
-    const bool use_lanes = forced_kernel ? forced_kernel == 2 : nseg >= (size_t)ctx->num_sms * 168;
+    const bool use_lanes = forced_kernel ? forced_kernel == 2 : nseg >= (size_t)ctx->num_sms * 81;   // crossover measured at ~11 k segments
     if (use_lanes) CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
     CU(ctx->inf_carry.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
 

@@ -161,12 +161,12 @@ cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* s
     }();
     int S = forced;
     if (!S) {
-        // measured on B200 (profiles/r01i_inflate_lanes_sweep.txt): with enough segments to keep every SM's resident
-        // warps full, 32 per warp is fastest (issue slots are shared 32 ways); below that, 6 per warp trades issue
-        // efficiency for more warps in flight
+        // measured on B200 (profiles/r01i_inflate_sweep.txt, r01n_inflate_sweep.txt): with enough segments to keep every SM's resident
+        // warps full, 32 per warp is fastest (issue slots are shared 32 ways); below that, 16 per warp trades issue
+        // efficiency for more warps in flight (16384 segments: 58.5 GB/s at 16, 55.9 at 32, 33.9 at 6)
         int full = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, inflate_lanes_kernel, 32, lane_smem(32)) != cudaSuccess || full < 1) full = 1;
-        S = (size_t)P.nseg * 4 >= (size_t)num_sms * full * 32 * 3 ? 32 : 6;
+        S = (size_t)P.nseg * 4 >= (size_t)num_sms * full * 32 * 3 ? 32 : 16;
     }
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_lanes_kernel, 32, lane_smem(S)) != cudaSuccess || per_sm < 1) per_sm = 1;

@@ -96,7 +96,7 @@ struct Lane {
     uint32_t cp_rem;       // bytes of the current symbol not yet appended (incl. the pending unit)
     uint32_t pend_n;       // bytes of the pending unit, 0 = none
     int pend_kind;         // UnitKind
-    uint32_t pend_val;     // U_LIT: the byte, or two
+    uint32_t pend_val;     // U_LIT: one to four bytes
     uint32_t cp_D;         // U_MEM: distance
     uint64_t plo, phi;     // U_PAT: 16 bytes of the periodic sequence
     uint32_t ph, pd;       //        phase of the next unit, period
@@ -472,7 +472,8 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
     }
     // (b)
     const bool dec = L.cp_rem == pn;
-    int sym = 0, sym2 = -1;
+    int sym = 0;
+    uint32_t lits = 0, nlit = 0;
     uint32_t len = 0, d = 0;
     int derr = IE_OK;
     if (dec) {
@@ -491,12 +492,17 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
             }
         }
         if (sym < 256 && derr == IE_OK) {
-            // a second literal in the same step when the next code is one too (root-table codes only; most of a text
-            // stream's symbols are literals): a step then yields two bytes for a dozen more instructions
-            const uint32_t e2 = T.root_l[L.acc & ((1u << ROOT_L) - 1u)];
-            if (e2 >= 16u && e2 < (256u << 4) && (int)(e2 & 15u) <= L.nbits) {
+            // more literals in the same step while the next code is one too (root-table codes only; most of a text
+            // stream's symbols are literals): up to four bytes per step for a dozen instructions each
+            lits = (uint32_t)sym;
+            nlit = 1;
+#pragma unroll
+            for (int x = 1; x < 4; x++) {
+                const uint32_t e2 = T.root_l[L.acc & ((1u << ROOT_L) - 1u)];
+                if (!(e2 >= 16u && e2 < (256u << 4) && (int)(e2 & 15u) <= L.nbits)) break;
                 drop(L, (int)(e2 & 15u));
-                sym2 = (int)(e2 >> 4);
+                lits |= (e2 >> 4) << (8 * x);
+                nlit = (uint32_t)x + 1;
             }
         }
         if (sym > 256 && derr == IE_OK) {
@@ -578,12 +584,11 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
     L.pend_n = 0;
     if (derr != IE_OK) return lane_fail(L, derr);
     if (sym < 256) {
-        const uint32_t nl = sym2 >= 0 ? 2u : 1u;
-        if (L.v + nl > L.vcap) return lane_fail(L, IE_OUTPUT_OVERFLOW);
+        if (L.v + nlit > L.vcap) return lane_fail(L, IE_OUTPUT_OVERFLOW);
         L.pend_kind = U_LIT;
-        L.pend_val = (uint32_t)sym | (sym2 >= 0 ? (uint32_t)sym2 << 8 : 0u);
-        L.pend_n = nl;
-        L.cp_rem = nl;
+        L.pend_val = lits;
+        L.pend_n = nlit;
+        L.cp_rem = nlit;
         return;
     }
     if (sym == 256) {

@@ -450,14 +450,21 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     const uint32_t max_blocks = (uint32_t)(seg_size / BLOCK_SYMS + 2);
     const size_t per_seg = sym_bytes_per_seg + max_blocks * (sizeof(BlockRec) + sizeof(BlockCodesDev)) + sizeof(uint32_t) + sizeof(SegLayout);
     size_t budget = env_size("ZSB_SCRATCH_BYTES", (size_t)8 << 30);
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        const size_t have = free_b + ctx->sym.cap + ctx->blocks.cap + ctx->codes.cap;
-        if (budget > have / 2) budget = have / 2;
-    }
     size_t batch = budget / per_seg;
     if (batch < 1) batch = 1;
     if (batch > nseg) batch = nseg;
+    if (ctx->sym.cap < batch * sym_bytes_per_seg) {
+        // the scratch has to grow: clamp the budget to half of what the device can still give (the query costs up to
+        // milliseconds on a busy box, so it is not made when the scratch of an earlier call is already big enough)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t have = free_b + ctx->sym.cap + ctx->blocks.cap + ctx->codes.cap;
+            if (budget > have / 2) budget = have / 2;
+        }
+        batch = budget / per_seg;
+        if (batch < 1) batch = 1;
+        if (batch > nseg) batch = nseg;
+    }
     // Host buffers: a few batches, so that the upload of batch b + 1 and the download of batch b - 1's output run beside the
     // kernels of batch b.  Batches are whole multiples of the SM count (the LZ77 kernels hand out one segment per SM at a time).
     bool piped = false;

@@ -348,16 +348,6 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                         if (sym < 256) {
                             if (o >= o_cap) { a = IE_OUTPUT_OVERFLOW; break; }
                             out[o++] = (uint8_t)sym;
-                            // The literals that follow, while they are root-table codes and fit in what the refill
-                            // left: no refill test, no long-code path, no loop-back through the symbol dispatch.  (The
-                            // kernel is issue-bound: 32 instructions per literal through the main loop, ~17 here.)
-#pragma unroll 1
-                            for (int x = 0; x < 3; x++) {
-                                const uint32_t e2 = t.fast_l[br.acc & ((1u << FAST_L) - 1)];
-                                if (!(e2 >= 16u && e2 < (256u << 4) && (int)(e2 & 15u) <= br.nbits) || o >= o_cap) break;
-                                br.drop((int)(e2 & 15u));
-                                out[o++] = (uint8_t)(e2 >> 4);
-                            }
                             continue;
                         }
                         if (sym == 256) { op = OP_EOB; break; }

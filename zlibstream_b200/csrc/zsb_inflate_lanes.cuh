@@ -39,6 +39,10 @@ constexpr int ROOT_L = ZSB_LN_ROOT_L;   // literal/length root table bits
 #define ZSB_LN_ROOT_D 6
 #endif
 constexpr int ROOT_D = ZSB_LN_ROOT_D;   // distance root table bits
+#ifndef ZSB_LN_LIT_STREAK
+#define ZSB_LN_LIT_STREAK 4
+#endif
+constexpr int LIT_STREAK = ZSB_LN_LIT_STREAK;   // literals taken in one step (<= 8: they travel in one 64-bit word)
 constexpr int ROOT_BL = 7;              // bit-length code: always complete within the root (MAX_BL_BITS)
 #ifndef ZSB_LN_LONG_L
 #define ZSB_LN_LONG_L 96
@@ -96,7 +100,7 @@ struct Lane {
     uint32_t cp_rem;       // bytes of the current symbol not yet appended (incl. the pending unit)
     uint32_t pend_n;       // bytes of the pending unit, 0 = none
     int pend_kind;         // UnitKind
-    uint32_t pend_val;     // U_LIT: one to four bytes
+    uint64_t pend_val;     // U_LIT: one to LIT_STREAK bytes
     uint32_t cp_D;         // U_MEM: distance
     uint64_t plo, phi;     // U_PAT: 16 bytes of the periodic sequence
     uint32_t ph, pd;       //        phase of the next unit, period
@@ -473,7 +477,8 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
     // (b)
     const bool dec = L.cp_rem == pn;
     int sym = 0;
-    uint32_t lits = 0, nlit = 0;
+    uint64_t lits = 0;
+    uint32_t nlit = 0;
     uint32_t len = 0, d = 0;
     int derr = IE_OK;
     if (dec) {
@@ -494,14 +499,15 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
         if (sym < 256 && derr == IE_OK) {
             // more literals in the same step while the next code is one too (root-table codes only; most of a text
             // stream's symbols are literals): up to four bytes per step for a dozen instructions each
-            lits = (uint32_t)sym;
+            lits = (uint64_t)sym;
             nlit = 1;
 #pragma unroll
-            for (int x = 1; x < 4; x++) {
+            for (int x = 1; x < LIT_STREAK; x++) {
+                if (x == 4) refill(L);
                 const uint32_t e2 = T.root_l[L.acc & ((1u << ROOT_L) - 1u)];
                 if (!(e2 >= 16u && e2 < (256u << 4) && (int)(e2 & 15u) <= L.nbits)) break;
                 drop(L, (int)(e2 & 15u));
-                lits |= (e2 >> 4) << (8 * x);
+                lits |= (uint64_t)(e2 >> 4) << (8 * x);
                 nlit = (uint32_t)x + 1;
             }
         }

@@ -10,7 +10,7 @@ import corpus_data
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "warp", "lanes"], autouse=True)
+@pytest.fixture(params=["auto", "warp", "lanes", "lanes_small"], autouse=True)
 def inflate_kernel(request, monkeypatch):
     """The library picks the warp-per-segment or the lane-per-segment inflate kernel from the number of segments; the
     parity tests run with the automatic choice and with each kernel forced (ZSB_INFLATE_KERNEL is read per call)."""

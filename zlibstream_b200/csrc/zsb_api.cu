@@ -680,12 +680,12 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     CU(cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned int), st));
     // Two kernels (profiles/r01i_inflate_sweep.txt, r01n_inflate_sweep.txt): a warp per segment decodes one segment fastest and wins while the
     // segments are few; a lane per segment shares every issued instruction 32 ways and wins once there are enough
-    // segments to fill the SMs' resident warps.  ZSB_INFLATE_KERNEL=warp|lanes forces one of them.
+    // segments to fill the SMs' resident warps.  ZSB_INFLATE_KERNEL=warp|lanes|lanes_small forces one of them.
     const int forced_kernel = [] {   // read per call: the tests switch kernels at run time
         const char* e = getenv("ZSB_INFLATE_KERNEL");
-        return !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : 0;
+        return !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : strcmp(e, "lanes_small") == 0 ? 3 : 0;
     }();
-    const bool use_lanes = forced_kernel ? forced_kernel == 2 : nseg >= (size_t)ctx->num_sms * 81;   // crossover measured at ~11 k segments
+    const bool use_lanes = forced_kernel ? forced_kernel >= 2 : nseg >= (size_t)ctx->num_sms * 81;   // crossover measured at ~11 k segments
     if (use_lanes) CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
     CU(ctx->inf_carry.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
 
@@ -705,7 +705,10 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     I.seg_carry = ctx->inf_carry.as<uint32_t>();
     I.carry_flag = d_carry_flag;
     timing_mark(ctx, 2, true);
-    if (use_lanes) CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+    // beyond ~3 segments per lane of the default kernel's residency the small-table instance (12 warps per SM) is faster
+    const bool small_tables = forced_kernel ? forced_kernel == 3 : nseg >= (size_t)ctx->num_sms * 7 * 32 * 3;
+    if (use_lanes && small_tables) CU(launch_inflate_lanes_small(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+    else if (use_lanes) CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
     else CU(launch_inflate(I, ctx->num_sms, st));
     timing_mark(ctx, 2, false);
     ctx->launches++;

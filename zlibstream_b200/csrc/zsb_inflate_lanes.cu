@@ -9,7 +9,13 @@
 
 namespace zsb {
 
-using namespace lanes;
+using namespace ZSB_LN_NS;
+
+// names of this translation unit's kernel and launcher (zsb_inflate_lanes_small.cu renames them)
+#ifndef ZSB_LN_KERNEL
+#define ZSB_LN_KERNEL inflate_lanes_kernel
+#define ZSB_LN_LAUNCH launch_inflate_lanes
+#endif
 
 namespace {
 
@@ -28,7 +34,7 @@ __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 // segs_per_warp (S): lanes 0..S-1 decode a segment each, the others only help with the table builds.  Fewer segments
 // per warp = fewer divergent paths serialised per iteration and more warps for the same number of segments; the
 // launcher picks S from the number of segments so that the SMs have enough warps to hide latency.
-__global__ void __launch_bounds__(32) inflate_lanes_kernel(InflateParams P, uint8_t* scratch, int segs_per_warp)
+__global__ void __launch_bounds__(32) ZSB_LN_KERNEL(InflateParams P, uint8_t* scratch, int segs_per_warp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& sc = *reinterpret_cast<WarpScratch*>(smem);
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(32) inflate_lanes_kernel(InflateParams P, uint
     }
 }
 
+#ifndef ZSB_LN_SECONDARY
 // Q14: one warp per segment that opens with a carried run.
 __global__ void __launch_bounds__(256) inflate_carry_fixup_kernel(InflateParams P)
 {
@@ -144,12 +151,14 @@ size_t inflate_lanes_scratch_bytes(int num_sms)
     return (size_t)num_sms * 32 * 32 * SCRATCH_STRIDE;   // up to 32 resident CTAs per SM
 }
 
-cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream)
+#endif  // ZSB_LN_SECONDARY
+
+cudaError_t ZSB_LN_LAUNCH(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     if (P.nseg == 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem(32));
+        cudaError_t e = cudaFuncSetAttribute(ZSB_LN_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem(32));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -165,16 +174,16 @@ cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* s
         // warps full, 32 per warp is fastest (issue slots are shared 32 ways); below that, 16 per warp trades issue
         // efficiency for more warps in flight (16384 segments: 58.5 GB/s at 16, 55.9 at 32, 33.9 at 6)
         int full = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, inflate_lanes_kernel, 32, lane_smem(32)) != cudaSuccess || full < 1) full = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, ZSB_LN_KERNEL, 32, lane_smem(32)) != cudaSuccess || full < 1) full = 1;
         S = (size_t)P.nseg * 4 >= (size_t)num_sms * full * 32 * 3 ? 32 : 16;
     }
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_lanes_kernel, 32, lane_smem(S)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ZSB_LN_KERNEL, 32, lane_smem(S)) != cudaSuccess || per_sm < 1) per_sm = 1;
     int ctas = num_sms * per_sm;
     const int need = (int)((P.nseg + S - 1) / S);
     if (ctas > need) ctas = need;
     if ((size_t)ctas * 32 * SCRATCH_STRIDE > scratch_bytes) return cudaErrorInvalidValue;
-    inflate_lanes_kernel<<<ctas, 32, lane_smem(S), stream>>>(P, scratch, S);
+    ZSB_LN_KERNEL<<<ctas, 32, lane_smem(S), stream>>>(P, scratch, S);
     return cudaGetLastError();
 }
 

@@ -27,7 +27,12 @@
 #include "zsb_kernels.cuh"
 
 namespace zsb {
-namespace lanes {
+// ZSB_LN_NS: the translation unit zsb_inflate_lanes_small.cu builds a second instance of everything below with smaller
+// tables (more resident warps, for inputs with far more segments than resident lanes) in its own namespace.
+#ifndef ZSB_LN_NS
+#define ZSB_LN_NS lanes
+#endif
+namespace ZSB_LN_NS {
 
 #define ZL_HD __host__ __device__ __forceinline__
 
@@ -866,5 +871,5 @@ ZL_HD void after_build(Lane& L, bool ld, int rc_l, int rc_d)
     L.st = S_SYM;
 }
 
-}  // namespace lanes
+}  // namespace ZSB_LN_NS
 }  // namespace zsb

@@ -111,6 +111,8 @@ cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t str
 // Lane-per-segment kernel (zsb_inflate_lanes.cu): the default.  scratch: inflate_lanes_scratch_bytes(num_sms) bytes.
 size_t inflate_lanes_scratch_bytes(int num_sms);
 cudaError_t launch_inflate_lanes(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream);
+// Same kernel with smaller per-lane tables (zsb_inflate_lanes_small.cu): more resident warps, for very many segments.
+cudaError_t launch_inflate_lanes_small(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream);
 // Q14 fix-up after the lane kernel: fills the carried leading bytes of Rle segments.
 cudaError_t launch_inflate_carry_fixup(const InflateParams& P, cudaStream_t stream);
 // Lists the end offset of every 00 00 FF FF inside in[begin, end) (unordered; *ncand may exceed cand_cap).

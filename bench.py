@@ -17,6 +17,10 @@ import sys
 import threading
 import time
 
+# stdout carries the ONE JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) out of it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))

@@ -17,9 +17,10 @@ import sys
 import threading
 import time
 
-# stdout carries the ONE JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries the ONE JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION / WARN) out of it
+# (VERSION and WARN both print it; an explicit INFO / TRACE of the caller is respected)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

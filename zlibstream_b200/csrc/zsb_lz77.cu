@@ -209,14 +209,24 @@ __device__ void fast_step(const Smem& sm, ParserState& s, const SegOut& o, const
 // Compare256 amount to: a candidate replaces the best match iff this value exceeds best_len).
 __device__ __forceinline__ int common_prefix258(const uint8_t* win, int p, int c)
 {
+    // eight bytes per step: three aligned words per side and two funnel shifts instead of two x (two words, one shift)
     int len = 0;
     while (len < MAX_MATCH + 2) {
-        const uint32_t x = lds_u32_unaligned(win, p + len) ^ lds_u32_unaligned(win, c + len);
-        if (x) {
-            len += (__ffs(x) - 1) >> 3;
+        const uint32_t* qa = reinterpret_cast<const uint32_t*>(win + ((p + len) & ~3));
+        const uint32_t* qb = reinterpret_cast<const uint32_t*>(win + ((c + len) & ~3));
+        const int sa = ((p + len) & 3) * 8, sb = ((c + len) & 3) * 8;
+        const uint32_t a0 = qa[0], a1 = qa[1], a2 = qa[2], b0 = qb[0], b1 = qb[1], b2 = qb[2];
+        const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+        if (x0) {
+            len += (__ffs(x0) - 1) >> 3;
             break;
         }
-        len += 4;
+        const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+        if (x1) {
+            len += 4 + ((__ffs(x1) - 1) >> 3);
+            break;
+        }
+        len += 8;
     }
     return len < MAX_MATCH ? len : MAX_MATCH;
 }

@@ -61,6 +61,39 @@ class Oracle:
         assert rc == 0, rc
         return out.raw[:n.value], list(ends[:nseg]), ad.value
 
+    def deflate_segments_parallel(self, data, seg_size, level, strategy=0, hv=0, threads=None):
+        """deflate_segments on several host threads (ctypes releases the GIL): the stream is cut into contiguous ranges
+        of segments, every range after the first is compressed with its PRECEDING segment in front (so the window, the
+        Rle halo byte and "not the stream's first segment" are what the single stream has) and that
+        segment's output is dropped.  tests/test_oracle_golden.py checks it equals the one-thread call."""
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(data)
+        nseg = (n + seg_size - 1) // seg_size
+        threads = threads or min(32, os.cpu_count() or 1)
+        per = max(4, (nseg + threads - 1) // threads)
+        cuts = list(range(0, nseg, per)) + [nseg]
+        if nseg <= per or len(cuts) < 3:
+            return self.deflate_segments(data, seg_size, level, strategy, hv)
+
+        def work(ab):
+            a, b = ab
+            lo = (a - 1) * seg_size if a else 0
+            out, ends, _ = self.deflate_segments(data[lo:min(b * seg_size, n)], seg_size, level, strategy, hv)
+            if a == 0:
+                return out[:ends[-1]], ends
+            return out[ends[0]:ends[-1]], [e - ends[0] for e in ends[1:]]
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            parts = list(ex.map(work, zip(cuts[:-1], cuts[1:])))
+        stream, all_ends, base = [], [], 0
+        for piece, ends in parts:
+            stream.append(piece)
+            all_ends += [base + e for e in ends]
+            base += len(piece)
+        adler = zlib.adler32(data) & 0xFFFFFFFF
+        return b"".join(stream) + b"\x03\x00" + adler.to_bytes(4, "big"), all_ends, adler
+
     def trace_segments(self, data, seg_size, level, strategy=0, hv=0):
         """Runs the segmented compressor with the block trace on.
         -> (stream, ends, per-segment list of blocks: dict(type, n, stored_len, bit_start, sym=[(dist, lc)...]))"""

@@ -296,3 +296,54 @@ def test_piped_host_path_equals_device_path(engine, corpus):
         got, ends, adler = engine.deflate_segments(data, seg, level, strategy)
         assert len(got) == len(want) and got == want, (level, strategy)
         assert ends == d_ends.cpu().tolist() and adler == d_adler == zlib.adler32(data)
+
+
+# ---- parity where the numbers are taken: several segments per CTA of the persistent kernels ---------------------------
+
+def _multiwave_input(kind, n):
+    """Deterministic inputs in the tens of megabytes, built by tiling + perturbing the small generators (every segment
+    differs from the others, so a stale window / hash table / tile buffer of the previous segment would show)."""
+    rng = np.random.RandomState(77)
+    if kind == "text":
+        base = corpus_data.text_like(4 << 20, seed=21)
+    elif kind == "mixed":
+        base = corpus_data.mixed_entropy(5 * 262144 * 3, seed=22)
+    else:
+        base = corpus_data.png_like(4 << 20, seed=23)
+    a = np.frombuffer(base, dtype=np.uint8)
+    reps = (n + a.size - 1) // a.size
+    out = np.tile(a, reps)[:n].copy()
+    # one random byte changed about every 4 KiB, so that the copies of the base are not identical segments
+    pos = rng.randint(0, n, size=n // 4096)
+    out[pos] = rng.randint(0, 256, size=pos.size).astype(np.uint8)
+    return out.tobytes()
+
+
+MULTIWAVE = [
+    # (name, data kind, segment size, #segments, level, strategy): >= 3 x 148 segments of 64 KiB, >= 2 x 148 of 256 KiB
+    ("L1-64K", "text", 65536, 460, 1, 0), ("L3-64K", "text", 65536, 460, 3, 0), ("L6-64K", "text", 65536, 460, 6, 0),
+    ("L9-64K", "text", 65536, 460, 9, 0), ("Filtered-64K", "png", 65536, 460, 6, 1), ("Rle-64K", "png", 65536, 460, 6, 3),
+    ("HuffmanOnly-64K", "png", 65536, 460, 6, 2), ("L1-256K", "mixed", 262144, 310, 1, 0),
+    ("L6-256K", "mixed", 262144, 310, 6, 0), ("L9-256K", "text", 262144, 310, 9, 0), ("Rle-256K", "png", 262144, 310, 6, 3),
+    ("L2-64K-mixed", "mixed", 65536, 460, 2, 0),
+]
+
+
+@pytest.mark.parametrize("name,kind,ss,nseg,level,strategy", MULTIWAVE, ids=[m[0] for m in MULTIWAVE])
+def test_multiwave_parity_with_the_oracle(engine, oracle, name, kind, ss, nseg, level, strategy):
+    """The LZ77 kernels are persistent (grid = #SMs, dynamic work counter): with more than 3 x 148 segments every CTA
+    parses several segments back to back, so state carried from one to the next (window, head / prev, slot table,
+    tile buffers, pipeline flags -- what a full flush does and does not reset, Deflate.cs:583-614) is compared with the
+    oracle bit for bit.  The same streams are then decoded by both inflate kernels."""
+    data = _multiwave_input(kind, ss * nseg + 1234)
+    want, want_ends, want_adler = oracle.deflate_segments_parallel(data, ss, level, strategy)
+    got, ends, adler = engine.deflate_segments(data, ss, level, strategy)
+    assert len(got) == len(want) and hashlib.sha256(got).digest() == hashlib.sha256(want).digest()
+    assert ends == want_ends and adler == want_adler
+    for kernel in ("warp", "lanes"):
+        os.environ["ZSB_INFLATE_KERNEL"] = kernel
+        try:
+            dec, dad = engine.inflate_segments(want, want_ends, ss, len(data))
+        finally:
+            del os.environ["ZSB_INFLATE_KERNEL"]
+        assert dad == want_adler and dec == data, (name, kernel)

@@ -199,3 +199,24 @@ def test_stream_class_argument_behaviour(engine):
     z.write(b"")
     z.close()
     assert sink.getvalue().hex() == "789c030000000001"      # empty stream: header, final empty static block, Adler(1)
+
+
+def test_undersized_output_capacity_is_refused_without_overrun(engine, oracle, corpus):
+    """out_cap two and a half segments short: every inflate kernel must stop at the caller's capacity (the bytes beyond
+    it keep their guard pattern) and the call must fail with ZBUFERROR, not write a full segment past the buffer."""
+    import torch
+    from zlibstream_b200 import ZlibStreamException
+    ss = 65536
+    data = (corpus["lcet10.txt"] + corpus["plrabn12.txt"])[:9 * ss + 100]
+    comp, ends, _ = oracle.deflate_segments(data, ss, 6)
+    d_comp = torch.frombuffer(bytearray(comp), dtype=torch.uint8).cuda()
+    d_ends = torch.tensor(ends, dtype=torch.int64, device="cuda")
+    cap = len(data) - 2 * ss - ss // 2
+    buf = torch.full((len(data) + ss,), 0xA5, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ZlibStreamException, match="inflating: "):
+        engine.inflate_segments_device(d_comp.data_ptr(), len(comp), d_ends.data_ptr(), len(ends), ss, buf.data_ptr(), cap)
+    assert engine._lib.zsb_last_error(engine._h) is not None
+    assert bool((buf[cap:] == 0xA5).all())
+    assert bytes(buf[:4 * ss].cpu().numpy()) == data[:4 * ss]      # the segments that fit are still decoded
+    with pytest.raises(ZlibStreamException, match="inflating: "):  # host-buffer path: same refusal
+        engine.inflate_segments(comp, ends, ss, cap)

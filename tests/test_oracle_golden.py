@@ -115,3 +115,15 @@ def test_level0_and_strategies_round_trip(oracle, corpus):
     for (lvl, st, want) in [(6, 1, 55812), (6, 2, 87918), (6, 3, 87611), (1, 4, 85028), (6, 4, 71716)]:
         out, _ = oracle.deflate_oneshot(a, lvl, st)
         assert len(out) == want and zlib.decompress(out) == a
+
+
+@pytest.mark.parametrize("level,strategy,ss", [(1, 0, 65536), (6, 0, 65536), (6, 3, 65536), (6, 2, 65536), (9, 1, 131072),
+                                               (3, 0, 262144)])
+def test_parallel_oracle_equals_the_single_thread_call(oracle, corpus, level, strategy, ss):
+    """oracle_lib.deflate_segments_parallel (used by the multi-wave GPU parity tests and bench.py's parity check) must
+    be the same function as zso_deflate_segments: ranges compressed behind their preceding segment."""
+    blob = b"".join(corpus[k] for k in sorted(corpus))
+    data = (blob + corpus_data.png_like(400000) + bytes(70000) + blob[::-1])[:22 * ss + 4321]
+    want = oracle.deflate_segments(data, ss, level, strategy)
+    got = oracle.deflate_segments_parallel(data, ss, level, strategy, threads=5)
+    assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]

@@ -737,6 +737,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         produced += lens[k];
     }
     if (out_len) *out_len = produced;
+    if (produced > out_cap) return fail(ctx, ZSB_BUF_ERROR, "buffer error");   // never reached: the kernels stop at out_cap
     if (carry_flag) {   // Q14: Rle segments that open with a run of the previous segment's last byte
         CU(launch_inflate_carry_fixup(I, st));
         ctx->launches++;

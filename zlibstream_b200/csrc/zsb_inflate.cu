@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
         const uint64_t c_begin = seg == 0 ? P.first_offset : P.seg_end[seg - 1];
         const uint64_t c_end = P.seg_end[seg];
         const uint64_t o_begin = (uint64_t)seg * P.seg_size;
-        const uint32_t o_cap = (uint32_t)((P.out_cap - o_begin) < P.seg_size ? (P.out_cap - o_begin) : P.seg_size);
+        const uint64_t o_room = o_begin < P.out_cap ? P.out_cap - o_begin : 0;   // never past the caller's buffer
+        const uint32_t o_cap = (uint32_t)(o_room < P.seg_size ? o_room : P.seg_size);
         uint8_t* out = P.out + o_begin;
         uint32_t o = 0;
         uint32_t carry = 0;   // Q14: leading bytes that repeat the previous segment's last byte (Rle streams)
@@ -446,11 +447,10 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
 cudaError_t launch_inflate(const InflateParams& P, int num_sms, cudaStream_t stream)
 {
     if (P.nseg == 0) return cudaSuccess;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_segments_kernel, INF_THREADS, 0) != cudaSuccess || per_sm < 1)
-            per_sm = 4;
-    }
+    // queried per call: the answer belongs to the current device, and a process may hold contexts on several
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_segments_kernel, INF_THREADS, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
     int ctas = num_sms * per_sm;   // persistent: every resident warp pulls segments from the work counter
     const int need = (int)((P.nseg + INF_GROUPS - 1) / INF_GROUPS);
     if (ctas > need) ctas = need;

@@ -156,11 +156,9 @@ size_t inflate_lanes_scratch_bytes(int num_sms)
 cudaError_t ZSB_LN_LAUNCH(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     if (P.nseg == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // a per-device attribute: set on every launch (a process may drive several GPUs, one zsb_ctx each)
         cudaError_t e = cudaFuncSetAttribute(ZSB_LN_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem(32));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     // Segments per warp: as many as still leave ~kWarpsWanted warps per SM (ZSB_INFLATE_SEGS_PER_WARP overrides).
     const int forced = [] {

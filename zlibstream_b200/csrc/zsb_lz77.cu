@@ -1471,14 +1471,12 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
     // ZSB_NO_SYMBOLIZE=1 keeps HuffmanOnly / Rle on the serial path below (A/B measurements, parity cross-checks)
     static const bool no_symbolize = getenv("ZSB_NO_SYMBOLIZE") != nullptr;
     if (!no_symbolize && !P.stats && symbolize_applies(P)) return launch_symbolize(P, num_sms, stream);
-    static bool configured = false;
     const size_t smem = lz77_smem_bytes(256), smem_wide = lz77_smem_bytes(1024);
-    if (!configured) {
+    {   // per-device attributes: set on every launch (a process may drive several GPUs, one zsb_ctx each)
         cudaError_t e = cudaFuncSetAttribute(lz77_segments_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(lz77_segments_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     int grid = (int)(P.nseg < (uint32_t)num_sms ? P.nseg : (uint32_t)num_sms);
     if (grid < 1) grid = 1;

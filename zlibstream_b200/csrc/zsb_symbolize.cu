@@ -402,11 +402,9 @@ bool symbolize_applies(const Lz77Params& P)
 cudaError_t launch_symbolize(const Lz77Params& P, int num_sms, cudaStream_t stream)
 {
     const size_t smem = (size_t)(P.seg_size / 32) * 20;
-    static size_t configured = 0;
-    if (smem > configured) {
+    {   // a per-device attribute: set on every launch (a process may drive several GPUs, one zsb_ctx each)
         cudaError_t e = cudaFuncSetAttribute(symbolize_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, symbolize_segments_kernel, SY_THREADS, smem) != cudaSuccess || per_sm < 1)

@@ -196,6 +196,33 @@ static uint8_t* run(const uint8_t* in, size_t n, size_t seg, int level, int use_
     return out;
 }
 
+/* The 32-byte records of kernel A for one segment (tools/l1_diag.py diffs the device's records against these).
+ * Build as a library:  gcc -O2 -shared -fPIC -DABM_LIB -o tools/ab_model/libabmodel.so tools/ab_model/ab_model.c oracle/zso_adler32.c */
+int abm_records(const uint8_t* seg, int n, int hash_variant, uint8_t* out)
+{
+    zso_deflater* d = zso_deflater_new(1, 0, ZSO_FULL_FLUSH, hash_variant);
+    if (!d || n > MAXSEG) return -1;
+    K = 10;
+    M.seg = seg;
+    M.N = n;
+    kernel_a(d);
+    for (int a = 0; a < n; a++) {
+        uint8_t* r = out + (size_t)a * 32;
+        memset(r, 0, 32);
+        for (int k = 0; k < M.nk[a]; k++) {
+            unsigned dd = M.dist[a][k] | (M.len[a][k] >= 3 ? 0x8000u : 0u);
+            r[2 * k] = (uint8_t)dd;
+            r[2 * k + 1] = (uint8_t)(dd >> 8);
+            r[20 + k] = (uint8_t)(M.len[a][k] >= 3 ? M.len[a][k] - 3 : 0);
+        }
+        r[30] = (uint8_t)(M.nk[a] | (M.more[a] << 7));
+        r[31] = seg[a];
+    }
+    zso_deflater_free(d);
+    return 0;
+}
+
+#ifndef ABM_LIB
 int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: ab_model file seg_size [K] [level]\n"); return 2; }
@@ -219,3 +246,4 @@ int main(int argc, char** argv)
            (double)st_overflow / (double)(st_search ? st_search : 1), (double)st_over_nodes / (double)(st_overflow ? st_overflow : 1));
     return same ? 0 : 1;
 }
+#endif

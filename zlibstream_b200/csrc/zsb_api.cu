@@ -78,7 +78,7 @@ struct zsb_ctx {
     std::string err;
     uint64_t launches = 0;
     // scratch
-    DevBuf in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry, idx_cand;
+    DevBuf lists, in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry, idx_cand;
     uint16_t* crc_tab = nullptr;
     unsigned long long* lz_stats = nullptr;  // 32 counters, only with ZSB_LZ_STATS=1
     // timing of the last call
@@ -330,7 +330,7 @@ void zsb_ctx_destroy(zsb_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&ctx->in_stage, &ctx->out_stage, &ctx->sym, &ctx->blocks, &ctx->nblocks, &ctx->codes, &ctx->layout,
+    DevBuf* bufs[] = {&ctx->lists, &ctx->in_stage, &ctx->out_stage, &ctx->sym, &ctx->blocks, &ctx->nblocks, &ctx->codes, &ctx->layout,
                       &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status, &ctx->inf_scratch, &ctx->inf_carry, &ctx->idx_cand};
     for (DevBuf* b : bufs) b->release();
     if (ctx->crc_tab) cudaFree(ctx->crc_tab);
@@ -439,7 +439,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     int* d_status = reinterpret_cast<int*>(small + 8);
     uint32_t* d_adler = reinterpret_cast<uint32_t*>(small + 12);
     unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
-    struct { uint64_t total; int status; uint32_t adler; uint32_t work; } init = {write_header ? 2u : 0u, 0, 1u, 0u};
+    struct { uint64_t total; int status; uint32_t adler; uint32_t work[3]; } init = {write_header ? 2u : 0u, 0, 1u, {0u, 0u, 0u}};
     CU(cudaMemcpyAsync(small, &init, sizeof init, cudaMemcpyHostToDevice, st));
     if (out_cap < (size_t)(write_header ? 2 : 0)) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
 
@@ -448,17 +448,33 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     // ---- batches of segments: bounded symbol scratch ----
     const size_t sym_bytes_per_seg = seg_size * sizeof(uint32_t);
     const uint32_t max_blocks = (uint32_t)(seg_size / BLOCK_SYMS + 2);
-    const size_t per_seg = sym_bytes_per_seg + max_blocks * (sizeof(BlockRec) + sizeof(BlockCodesDev)) + sizeof(uint32_t) + sizeof(SegLayout);
-    size_t budget = env_size("ZSB_SCRATCH_BYTES", (size_t)8 << 30);
+    const LevelCfg cfg = kLevels[level];
+    // level 1 runs as two kernels with 32 bytes of candidate records per input byte between them (zsb_lz77_lists.cu)
+    bool use_lists = false;
+    {
+        Lz77Params probe{};
+        probe.lists = reinterpret_cast<uint4*>(1);
+        probe.seg_size = (uint32_t)seg_size;
+        probe.strategy = strategy;
+        probe.good = cfg.good; probe.lazy = cfg.lazy; probe.nice = cfg.nice; probe.chain = cfg.chain;
+        probe.fn = strategy == ZSB_RLE ? FN_RLE : cfg.fn;
+        probe.stats = ctx->lz_stats;
+        const char* l1 = getenv("ZSB_L1_KERNEL");
+        use_lists = lz77_lists_applies(probe) && !(l1 && strcmp(l1, "batch") == 0);
+    }
+    const size_t list_bytes_per_seg = use_lists ? lz77_lists_bytes_per_segment((uint32_t)seg_size) : 0;
+    const size_t per_seg = sym_bytes_per_seg + list_bytes_per_seg + max_blocks * (sizeof(BlockRec) + sizeof(BlockCodesDev)) + sizeof(uint32_t) + sizeof(SegLayout);
+    // the resolve kernel parses one segment per warp: a batch should hold a few thousand segments (5 k resident warps on B200)
+    size_t budget = env_size("ZSB_SCRATCH_BYTES", use_lists ? (size_t)48 << 30 : (size_t)8 << 30);
     size_t batch = budget / per_seg;
     if (batch < 1) batch = 1;
     if (batch > nseg) batch = nseg;
-    if (ctx->sym.cap < batch * sym_bytes_per_seg) {
+    if (ctx->sym.cap < batch * sym_bytes_per_seg || ctx->lists.cap < batch * list_bytes_per_seg) {
         // the scratch has to grow: clamp the budget to half of what the device can still give (the query costs up to
         // milliseconds on a busy box, so it is not made when the scratch of an earlier call is already big enough)
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t have = free_b + ctx->sym.cap + ctx->blocks.cap + ctx->codes.cap;
+            const size_t have = free_b + ctx->sym.cap + ctx->blocks.cap + ctx->codes.cap + ctx->lists.cap;
             if (budget > have / 2) budget = have / 2;
         }
         batch = budget / per_seg;
@@ -488,13 +504,13 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     uint64_t copied_to = hdr_bytes;   // host output bytes [hdr_bytes, copied_to) are already on their way
     if (nseg) {
         CU(ctx->sym.reserve(batch * sym_bytes_per_seg));
+        if (use_lists) CU(ctx->lists.reserve(batch * list_bytes_per_seg));
         CU(ctx->blocks.reserve(batch * max_blocks * sizeof(BlockRec)));
         CU(ctx->codes.reserve(batch * max_blocks * sizeof(BlockCodesDev)));
         CU(ctx->nblocks.reserve(batch * sizeof(uint32_t)));
         CU(ctx->layout.reserve(batch * sizeof(SegLayout)));
     }
 
-    const LevelCfg cfg = kLevels[level];
     int bidx = 0;
     for (size_t s0 = 0; s0 < nseg; s0 += batch, bidx++) {
         const uint32_t cnt = (uint32_t)((nseg - s0) < batch ? (nseg - s0) : batch);
@@ -521,7 +537,8 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         L.work_counter = d_work;
         L.crc_tab = ctx->crc_tab;
         L.stats = ctx->lz_stats;
-        CU(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+        L.lists = use_lists ? ctx->lists.as<uint4>() : nullptr;
+        CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
         timing_mark(ctx, 0, true);
         CU(launch_lz77(L, ctx->num_sms, st));
         timing_mark(ctx, 0, false);
@@ -844,6 +861,7 @@ extern "C" ZSB_API int zsb_debug_fetch(zsb_ctx* ctx, int what, uint64_t byte_off
         case 3: b = &ctx->layout; break;     // SegLayout [seg]
         case 4: b = &ctx->codes; break;      // BlockCodesDev [seg][max_blocks]
         case 5: b = &ctx->seg_adler; break;  // uint2 [seg]
+        case 7: b = &ctx->lists; break;      // level 1 candidate records, 32 bytes per input byte of the last batch
         case 6: {                            // LZ77 diagnostics counters (ZSB_LZ_STATS=1), cumulative
             if (!ctx->lz_stats || byte_offset + bytes > 32 * sizeof(unsigned long long)) return fail(ctx, ZSB_BUF_ERROR, "no stats");
             CU(cudaSetDevice(ctx->device));

@@ -24,7 +24,15 @@ struct Lz77Params {
     unsigned int* work_counter;
     const uint16_t* crc_tab;  // 4 * 256
     unsigned long long* stats; // optional diagnostics counters (ZSB_LZ_STATS=1), else nullptr
+    // level 1, two-kernel path (zsb_lz77_lists.cu + zsb_lz77_resolve.cu): 32-byte candidate records, [nseg][seg_size] x 2 uint4;
+    // nullptr = not available (the batch parser of zsb_lz77.cu runs instead).  work_counter then points to three counters.
+    uint4* lists = nullptr;
 };
+constexpr int LZ_LIST_K = 10;          // candidates per record
+bool lz77_lists_applies(const Lz77Params& P);
+size_t lz77_lists_bytes_per_segment(uint32_t seg_size);
+cudaError_t launch_lz77_lists(const Lz77Params& P, int num_sms, cudaStream_t stream);     // kernel A: records + Adler sums
+cudaError_t launch_lz77_resolve(const Lz77Params& P, int num_sms, cudaStream_t stream);   // kernel B: symbols + block records
 size_t lz77_smem_bytes();
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream);
 // HuffmanOnly and Rle need no hash chains: zsb_symbolize.cu produces their symbols, blocks and Adler sums in parallel.

@@ -63,7 +63,7 @@ static void kernel_a(const zso_deflater* s)
         M.prev_all[a] = head_all[h];
         head_all[h] = a;
         int c = M.prev_all[a], k = 0;
-        while (c >= 0 && a - c <= MAXD && k < K) {
+        while (c >= 0 && a - c <= (k == 0 ? MAXD : MAXD - 1) && k < K) {
             M.dist[a][k] = (uint16_t)(a - c);
             M.len[a][k] = (uint16_t)cp258(a, c);
             k++;
@@ -209,14 +209,17 @@ int abm_records(const uint8_t* seg, int n, int hash_variant, uint8_t* out)
     for (int a = 0; a < n; a++) {
         uint8_t* r = out + (size_t)a * 32;
         memset(r, 0, 32);
+        unsigned usem = 0;
         for (int k = 0; k < M.nk[a]; k++) {
-            unsigned dd = M.dist[a][k] | (M.len[a][k] >= 3 ? 0x8000u : 0u);
-            r[2 * k] = (uint8_t)dd;
-            r[2 * k + 1] = (uint8_t)(dd >> 8);
+            r[2 * k] = (uint8_t)M.dist[a][k];
+            r[2 * k + 1] = (uint8_t)(M.dist[a][k] >> 8);
             r[20 + k] = (uint8_t)(M.len[a][k] >= 3 ? M.len[a][k] - 3 : 0);
+            if (M.len[a][k] >= 3) usem |= 1u << k;
         }
-        r[30] = (uint8_t)(M.nk[a] | (M.more[a] << 7));
-        r[31] = seg[a];
+        /* bytes 30..31: ten flags "prefix >= 3", "the chain goes on", the number of candidates */
+        unsigned hi = usem | ((unsigned)M.more[a] << 10) | ((unsigned)M.nk[a] << 11);
+        r[30] = (uint8_t)hi;
+        r[31] = (uint8_t)(hi >> 8);
     }
     zso_deflater_free(d);
     return 0;

@@ -19,8 +19,10 @@ ABM.abm_records.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.
 
 def rec_str(r):
     d = struct.unpack("<10H", r[:20])
-    return " ".join(f"{x & 0x7FFF}{'*' if x >> 15 else ''}:{r[20 + k] + 3 if x >> 15 else 0}" for k, x in enumerate(d[:r[30] & 15])) + \
-        f" nk={r[30] & 15} more={r[30] >> 7} lit={r[31]}"
+    hi = r[30] | (r[31] << 8)
+    nk, more, usem = hi >> 11, (hi >> 10) & 1, hi & 0x3FF
+    return " ".join(f"{x}{'*' if (usem >> k) & 1 else ''}:{r[20 + k] + 3 if (usem >> k) & 1 else 0}" for k, x in enumerate(d[:nk])) + \
+        f" nk={nk} more={more}"
 
 
 def check_records(eng, data, seg, nseg_check=3):
@@ -45,12 +47,13 @@ def main():
     eng = Engine(0)
     import test_gpu_deflate as T
     corpus = corpus_data.load_corpus()
-    cases = [("smallscratch", T._run_lengths_data(9, 8 * 65536) + b"\x05" * 70000 + corpus_data.text_like(3 * 65536 + 1234, seed=3)),
+    blob = b"".join(corpus[k] for k in sorted(corpus))
+    cases = [("corpus_cat", blob), ("smallscratch", T._run_lengths_data(9, 8 * 65536) + b"\x05" * 70000 + corpus_data.text_like(3 * 65536 + 1234, seed=3)),
              ("runs1", T._run_lengths_data(1, 4 * 65536)),
              ("alice", corpus["alice29.txt"]),
              ("ptt5", corpus["ptt5"])]
     for name, data in cases:
-        for seg in (65536, 131072):
+        for seg in (65536, 262144):
             ok = gpu_diag.diff_case(eng, orc, name, data, seg, 1, 0)
             if not ok:
                 check_records(eng, data, seg)

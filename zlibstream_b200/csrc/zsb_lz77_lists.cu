@@ -18,8 +18,8 @@
 // memory); inside a group, equal hashes are found with 15 ballots.  Adler-32 partial sums are taken from the staged
 // bytes (no extra pass over the input).
 //
-// Record (32 bytes per position, HBM): 10 x u16 distance (bit 15: prefix >= 3), 10 x u8 (prefix - 3), u8 count |
-// "chain goes on" << 7, u8 the byte at the position (kernel B never reads the input except on its slow path).
+// Record (32 bytes per position, HBM): 10 x u16 distance, 10 x u8 (prefix - 3), then 16 bits: ten flags "prefix >= 3",
+// "the chain goes on", the number of candidates.
 #include "zsb_kernels.cuh"
 #include "zsb_lz77_dev.cuh"
 
@@ -173,8 +173,11 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                 const bool leader = below == 0, tail = (same >> lane) == 1u;
                 const int src = leader ? lane : 31 - __clz(below);
                 // -- ordered: InsertString of every position, in position order --
-                if (lane == 0)
-                    while (*turn != g) {}
+                if (lane == 0) {   // far from the turn: sleep (31 spinning warps would take the issue slots of the one that links)
+                    int tnow;
+                    while ((tnow = *turn) != g)
+                        if (g - tnow > 3) __nanosleep(g - tnow > 12 ? 400 : 100);
+                }
                 __syncwarp();
                 __threadfence_block();
                 uint32_t pred = leader ? (uint32_t)head[h] : 0u;
@@ -189,12 +192,17 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                 if (lane == 0) *turn = g + 1;
                 // -- the LK nearest predecessors and their common prefix lengths --
                 uint32_t dd[LZ_LIST_K], ll[LZ_LIST_K];
+                uint32_t usem = 0, edge = 0;
                 int total = 0, nk = 0;
 #pragma unroll
                 for (int k = 0; k < LZ_LIST_K; k++) {
                     dd[k] = 0;
                     ll[k] = 0;
-                    if (d != 0 && total + (int)d <= MAX_DIST) {
+                    // a node at exactly MAX_DIST can only be visited first (Deflate.cs:1031,1096): listed as candidate 0 only,
+                    // otherwise left to kernel B's chain walk ("the chain goes on")
+                    const bool inwin = d != 0 && total + (int)d <= MAX_DIST;
+                    if (inwin && k > 0 && total + (int)d == MAX_DIST) edge = 1u;
+                    if (inwin && (k == 0 || total + (int)d < MAX_DIST)) {
                         total += (int)d;
                         const int cidx = idx - total;
                         uint32_t useful = 0, L = 0;
@@ -211,13 +219,14 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                             useful = 1;
                             L = (uint32_t)(len - MIN_MATCH);
                         }
-                        dd[k] = (uint32_t)total | (useful << 15);
+                        dd[k] = (uint32_t)total;
+                        usem |= useful << k;
                         ll[k] = L;
                         nk = k + 1;
                         d = ring[(uint32_t)(a - total) % RING];
                     } else d = 0;
                 }
-                const uint32_t more = (d != 0 && total + (int)d <= MAX_DIST) ? 1u : 0u;
+                const uint32_t more = (d != 0 && total + (int)d <= MAX_DIST) ? 1u : edge;
                 uint4 r0, r1;
                 r0.x = dd[0] | (dd[1] << 16);
                 r0.y = dd[2] | (dd[3] << 16);
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                 r1.x = dd[8] | (dd[9] << 16);
                 r1.y = ll[0] | (ll[1] << 8) | (ll[2] << 16) | (ll[3] << 24);
                 r1.z = ll[4] | (ll[5] << 8) | (ll[6] << 16) | (ll[7] << 24);
-                r1.w = ll[8] | (ll[9] << 8) | (((uint32_t)nk | (more << 7)) << 16) | ((scan[0] & 0xFFu) << 24);
+                r1.w = ll[8] | (ll[9] << 8) | (usem << 16) | (more << 26) | ((uint32_t)nk << 27);
                 seg_rec[(size_t)a * 2] = r0;
                 seg_rec[(size_t)a * 2 + 1] = r1;
             }

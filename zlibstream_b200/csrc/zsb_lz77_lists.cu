@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                 if (lane == 0) {   // far from the turn: sleep (31 spinning warps would take the issue slots of the one that links)
                     int tnow;
                     while ((tnow = *turn) != g)
-                        if (g - tnow > 3) __nanosleep(g - tnow > 12 ? 400 : 100);
+                        if (g - tnow > 2) __nanosleep(g - tnow > 8 ? 800 : 100);   // measured flat around these values
                 }
                 __syncwarp();
                 __threadfence_block();

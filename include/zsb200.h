@@ -63,6 +63,7 @@ extern "C" {
 #define ZSB_NO_HEADER 0x4u      /* deflate: do not emit / inflate: do not expect the 2-byte zlib header   */
 #define ZSB_NO_TRAILER 0x8u     /* deflate: do not emit / inflate: do not expect `03 00` + Adler-32        */
 #define ZSB_OFFSETS_DEVICE 0x10u /* seg_end_offsets is a device pointer */
+#define ZSB_CONTINUATION 0x20u   /* inflate: `in` is a later shard of a stream (its first segment may open with a Q14 run) */
 
 typedef struct zsb_ctx zsb_ctx;
 
@@ -125,6 +126,20 @@ ZSB_API int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t 
 ZSB_API int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t* seg_end_offsets,
                                  size_t nseg, size_t seg_size, unsigned flags, void* out, size_t out_cap,
                                  size_t* out_len, uint32_t* adler);
+
+/*
+ * Q14 (Deflate.Rle.cs:47-50): an Rle segment may open with a distance-1 run of the byte BEFORE it.  Inside one call the
+ * library fills such runs from the previous segment; for the first segment of a call (a later shard of a stream) that byte
+ * is not in `in`: this returns how many leading output bytes of the last zsb_inflate_segments call were left unset, for the
+ * caller to fill with the last byte of the previous shard.
+ *
+ * zsb_inflate_fill_carry fills those bytes (and those of following segments that are one carried run from end to end) in the
+ * DEVICE output buffer of the last zsb_inflate_segments call with prev_byte and returns the Adler-32 of the completed output.
+ * A first segment may only open with such a run when the call was made with ZSB_CONTINUATION ("invalid distance too far back"
+ * otherwise, as at the start of a stream).
+ */
+ZSB_API int zsb_ctx_last_inflate_carry(const zsb_ctx* ctx, uint32_t* first_segment_carry);
+ZSB_API int zsb_inflate_fill_carry(zsb_ctx* ctx, uint8_t prev_byte, uint32_t* adler);
 
 /*
  * Segment index of a full-flush-segmented stream that comes without a side-car, e.g. one written by the reference itself

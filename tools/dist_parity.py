@@ -2,7 +2,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29544 tools/dist_parity.py
 Every rank compresses its contiguous range of segments, the exchange step gathers to rank 0, and rank 0 compares the gathered
 stream byte for byte with the oracle's single-stream output for the same input (level 1, level 6, Rle with its one-byte
-halo across ranks), then inflates it on the device without a side-car."""
+halo across ranks), then inflates it on the device without a side-car.  The gathered stream is then broadcast, every rank
+decodes its contiguous range of the segment index (inflate_sharded: Q14 carries cross ranks, Adler-32 folds with
+adler32_combine against the trailer) and rank 0 compares the gathered output with the input."""
 import os
 import sys
 
@@ -13,7 +15,7 @@ import torch.distributed as dist
 
 import corpus_data
 from zlibstream_b200 import Engine, adler32_combine
-from zlibstream_b200.dist import deflate_sharded, shard_segments
+from zlibstream_b200.dist import deflate_sharded, inflate_sharded, shard_index, shard_segments
 
 
 def main():
@@ -47,6 +49,40 @@ def main():
             ok = ok and dec == data and ad == want_adler
             print(f"world {world} level {level} strategy {strategy}: {'IDENTICAL' if ok else 'DIFFERENT'} ({len(got)} bytes)", flush=True)
             ok_all = ok_all and ok
+        dist.barrier()
+        # ---- sharded inflate of that stream: index and stream to every rank, each decodes its compressed-offset range ----
+        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            meta[0], meta[1] = res.total_len, res.adler
+        dist.broadcast(meta, 0)
+        total_len, want_adler = int(meta[0]), int(meta[1])
+        stream = gather[:total_len].clone() if rank == 0 else torch.empty(total_len, dtype=torch.uint8, device=dev)
+        dist.broadcast(stream, 0)
+        all_ends = [torch.empty_like(ends) for _ in range(world)] if (s1 - s0) * world == nseg else None
+        # segment ends of the whole stream: every rank's local ends + its scanned offset
+        sizes = torch.tensor(res.sizes, dtype=torch.int64)
+        offs = torch.tensor(res.offsets, dtype=torch.int64)
+        my = (ends[:s1 - s0] + int(offs[rank])).to(torch.int64)
+        cnt = torch.tensor([s1 - s0], dtype=torch.int64, device=dev)
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        pad = torch.zeros(max(int(c) for c in cnts), dtype=torch.int64, device=dev)
+        pad[:s1 - s0] = my
+        pads = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(pads, pad)
+        idx = torch.cat([p_[:int(c)] for p_, c in zip(pads, cnts)]).cpu().tolist()
+        b, e, clo, chi = shard_index(idx, 2, world, rank)
+        local_comp = stream[clo:chi].contiguous()
+        local_ends = torch.tensor([x - clo for x in idx[b:e]], dtype=torch.int64, device=dev)
+        dec = torch.zeros((e - b) * seg, dtype=torch.uint8, device=dev)
+        gout = torch.empty(len(data) + 16, dtype=torch.uint8, device=dev) if rank == 0 else torch.empty(1, dtype=torch.uint8, device=dev)
+        ires = inflate_sharded(eng, adler32_combine, local_comp, local_ends, seg, dec, has_header=(b == 0), expect_adler=want_adler,
+                               gather_to=gout)
+        if rank == 0:
+            oki = bytes(ires.out.cpu().numpy()) == data and ires.adler == want_adler
+            print(f"world {world} level {level} strategy {strategy}: sharded inflate {'IDENTICAL' if oki else 'DIFFERENT'} "
+                  f"(carry of rank shards folded: adler {ires.adler:08x})", flush=True)
+            ok_all = ok_all and oki
         dist.barrier()
     eng.close()
     dist.destroy_process_group()

@@ -10,12 +10,13 @@ ZSB_OUT_DEVICE = 0x2
 ZSB_NO_HEADER = 0x4
 ZSB_NO_TRAILER = 0x8
 ZSB_OFFSETS_DEVICE = 0x10
+ZSB_CONTINUATION = 0x20
 
 # every symbol include/zsb200.h declares
 EXPORTS = [
     "zsb_ctx_create", "zsb_ctx_destroy", "zsb_last_error", "zsb_ctx_set_stream", "zsb_ctx_get_stream",
     "zsb_ctx_launch_count", "zsb_ctx_last_kernel_ms", "zsb_deflate_bound", "zsb_deflate_segments",
-    "zsb_inflate_segments", "zsb_build_segment_index", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
+    "zsb_inflate_segments", "zsb_ctx_last_inflate_carry", "zsb_inflate_fill_carry", "zsb_build_segment_index", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
 ]
 
 _lib = None
@@ -58,6 +59,10 @@ def load():
     lib.zsb_deflate_segments.restype = i32
     lib.zsb_inflate_segments.argtypes = [vp, vp, sz, vp, sz, sz, c.c_uint, vp, sz, c.POINTER(sz), c.POINTER(u32)]
     lib.zsb_inflate_segments.restype = i32
+    lib.zsb_ctx_last_inflate_carry.argtypes = [vp, c.POINTER(u32)]
+    lib.zsb_ctx_last_inflate_carry.restype = i32
+    lib.zsb_inflate_fill_carry.argtypes = [vp, c.c_uint8, c.POINTER(u32)]
+    lib.zsb_inflate_fill_carry.restype = i32
     lib.zsb_build_segment_index.argtypes = [vp, vp, sz, sz, c.c_uint, vp, sz, c.POINTER(sz), c.POINTER(u64)]
     lib.zsb_build_segment_index.restype = i32
     lib.zsb_adler32.argtypes = [vp, u32, vp, sz, c.c_uint, c.POINTER(u32)]

@@ -77,6 +77,10 @@ struct zsb_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    uint32_t last_first_carry = 0;          // Q14: carried prefix of the first segment of the last inflate call
+    InflateParams last_inflate{};           // that call's parameters (device output only): zsb_inflate_fill_carry
+    size_t last_inflate_produced = 0;
+    bool last_inflate_valid = false;
     // scratch
     DevBuf lists, in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry, idx_cand;
     uint16_t* crc_tab = nullptr;
@@ -365,6 +369,37 @@ int zsb_ctx_last_kernel_ms(const zsb_ctx* cctx, float* lz, float* hf, float* inf
     if (lz) *lz = ctx->ms[0];
     if (hf) *hf = ctx->ms[1];
     if (inf) *inf = ctx->ms[2];
+    return ZSB_OK;
+}
+
+int zsb_ctx_last_inflate_carry(const zsb_ctx* ctx, uint32_t* first_segment_carry)
+{
+    if (!ctx || !first_segment_carry) return ZSB_STREAM_ERROR;
+    *first_segment_carry = ctx->last_first_carry;
+    return ZSB_OK;
+}
+
+int zsb_inflate_fill_carry(zsb_ctx* ctx, uint8_t prev_byte, uint32_t* adler)
+{
+    if (!ctx) return ZSB_STREAM_ERROR;
+    ctx->err.clear();
+    if (!ctx->last_inflate_valid) return fail(ctx, ZSB_STREAM_ERROR, "no inflate call with a device output to complete");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    InflateParams I = ctx->last_inflate;
+    I.prev_byte = prev_byte;
+    CU(launch_inflate_carry_fixup(I, st));
+    const size_t produced = ctx->last_inflate_produced;
+    const size_t achunks = (produced + kAdlerChunk - 1) / kAdlerChunk;
+    CU(ctx->seg_adler.reserve((achunks ? achunks : 1) * sizeof(uint2)));
+    uint32_t* d_adler = reinterpret_cast<uint32_t*>(ctx->small.as<uint8_t>() + 12);
+    CU(launch_adler32(I.out, produced, 1u, ctx->seg_adler.as<uint2>(), (uint32_t)(achunks ? achunks : 1), d_adler, st));
+    ctx->launches += 3;
+    uint32_t got = 1;
+    CU(cudaMemcpyAsync(&got, d_adler, sizeof got, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (adler) *adler = got;
+    ctx->last_first_carry = 0;
     return ZSB_OK;
 }
 
@@ -721,6 +756,8 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     I.work_counter = d_work;
     I.seg_carry = ctx->inf_carry.as<uint32_t>();
     I.carry_flag = d_carry_flag;
+    I.continuation = (flags & ZSB_CONTINUATION) ? 1 : 0;
+    ctx->last_inflate_valid = false;
     timing_mark(ctx, 2, true);
     // beyond ~3 segments per lane of the default kernel's residency the small-table instance (12 warps per SM) is faster
     const bool small_tables = forced_kernel ? forced_kernel == 3 : nseg >= (size_t)ctx->num_sms * 7 * 32 * 3;
@@ -755,9 +792,18 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     }
     if (out_len) *out_len = produced;
     if (produced > out_cap) return fail(ctx, ZSB_BUF_ERROR, "buffer error");   // never reached: the kernels stop at out_cap
+    ctx->last_first_carry = 0;
+    if (flags & ZSB_OUT_DEVICE) {
+        ctx->last_inflate = I;
+        ctx->last_inflate_produced = produced;
+        ctx->last_inflate_valid = true;
+    }
     if (carry_flag) {   // Q14: Rle segments that open with a run of the previous segment's last byte
         CU(launch_inflate_carry_fixup(I, st));
         ctx->launches++;
+        // the first segment of the call has nothing before it here: its carried prefix is the caller's to fill (sharded streams)
+        CU(cudaMemcpyAsync(&ctx->last_first_carry, ctx->inf_carry.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
     }
     // running Adler-32 of the output (InflateBlocks.cs:755,792) as a separate pass over the decoded bytes
     CU(launch_adler32(d_out, produced, 1u, ctx->seg_adler.as<uint2>(), (uint32_t)(achunks ? achunks : 1), d_adler, st));

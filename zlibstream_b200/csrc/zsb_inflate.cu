@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
                 if ((uint32_t)d > o || o - (uint32_t)d < carry) {
                     // Q14 (Deflate.Rle.cs:47-50): distance-1 runs of the previous segment's last byte open the segment;
                     // placeholders now, inflate_carry_fixup_kernel fills them in once every segment is decoded
-                    if (!(d == 1 && o == carry && seg > 0)) { err = IE_DIST_TOO_FAR; break; }
+                    if (!(d == 1 && o == carry && (seg > 0 || P.continuation))) { err = IE_DIST_TOO_FAR; break; }
                     for (int i = lane; i < a; i += GW) out[o + i] = 0;
                     carry += (uint32_t)a;
                     o += (uint32_t)a;

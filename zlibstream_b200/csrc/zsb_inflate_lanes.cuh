@@ -112,6 +112,7 @@ struct Lane {
     int count;             // count-only pass (segment index building): nothing is loaded from or stored to `out`
     uint32_t found;        // count-only: offset just past the full-flush marker that ended the piece, 0 = none yet
     uint32_t carry;        // Q14: leading bytes that repeat the previous segment's last byte (Rle streams only)
+    uint32_t carry_ok;     // this segment is not the stream's first: it may open with such a run
     uint64_t bl_lens;      // 19 x 3 bits
 };
 
@@ -611,7 +612,7 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
     if (d > o || o - d < L.carry) {
         // Q14 (Deflate.Rle.cs:47-50): an Rle segment may open with distance-1 runs of the previous segment's last byte.
         // Those bytes are placeholders here; inflate_carry_fixup_kernel fills them in once every segment is decoded.
-        if (!(d == 1 && o == L.carry && L.seg > 0)) return lane_fail(L, IE_DIST_TOO_FAR);
+        if (!(d == 1 && o == L.carry && L.carry_ok)) return lane_fail(L, IE_DIST_TOO_FAR);
         L.carry += len;
         L.pend_kind = U_ZERO;
     } else if (d <= 8) {
@@ -629,6 +630,7 @@ ZL_HD void sym_step(Lane& L, const LaneTables& T, const uint16_t* glong)
 ZL_HD void begin_segment(Lane& L, const InflateParams& P, uint32_t seg)
 {
     L.seg = seg;
+    L.carry_ok = (seg > 0 || P.continuation) ? 1u : 0u;
     L.err = IE_OK;
     L.st = S_BLOCK;
     L.pos = 0;
@@ -697,6 +699,12 @@ ZL_HD bool carry_fill_value(const InflateParams& P, uint32_t k, uint8_t& val)
             val = P.out[(uint64_t)j * P.seg_size + len - 1];
             return true;
         }
+    }
+    // every earlier segment of this call is a carried run from end to end: the byte before the call (known to the caller
+    // of a later shard, zsb_inflate_fill_carry), or nothing yet
+    if (P.prev_byte >= 0) {
+        val = (uint8_t)P.prev_byte;
+        return true;
     }
     return false;
 }

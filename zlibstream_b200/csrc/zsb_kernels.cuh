@@ -111,6 +111,8 @@ struct InflateParams {
     // seg_end[k-1] (first_offset for k = 0) and runs to the first empty stored block (the full-flush marker,
     // Deflate.cs:710-712), whose end offset goes to seg_found_end[k]; it may read up to count_body_end and produce at
     // most seg_size bytes
+    int continuation = 0;      // `in` does not start at the stream's first segment: segment 0 of the call may open with a Q14 run
+    int prev_byte = -1;        // carry fix-up: the byte before the call's first segment, once the caller knows it (else -1)
     int count_only = 0;
     uint64_t count_body_end = 0;
     uint64_t* seg_found_end = nullptr;

@@ -1,4 +1,4 @@
-"""Multi-GPU segmented deflate: one process per GPU, segments sharded contiguously across ranks.
+"""Multi-GPU segmented deflate and inflate: one process per GPU, segments sharded contiguously across ranks.
 
 The reference has no multi-process code at all; this is the exchange step the north star
 describes for full-flush segments, which are independent units of work:
@@ -10,10 +10,15 @@ describes for full-flush segments, which are independent units of work (SURVEY s
   4. variable-size gather of the compressed bytes to rank 0 (batched isend / irecv: NCCL has no gatherv);
   5. rank 0 folds the per-rank Adler-32 values with adler32_combine and appends `03 00` + the big-endian checksum.
 
-`engine` is anything with the Engine.deflate_segments_device signature (tests drive the host logic with a CPU
+Inflate shards the same way (last sentence): the segment index of the stream is cut into contiguous ranges of
+segments = contiguous compressed-offset ranges; every rank decodes its range, an all_gather of (decoded bytes, Adler-32,
+Q14 carry, last byte) gives every rank its output offset and the stream's checksum (adler32_combine fold, checked against
+the trailer), and the decoded bytes are optionally gathered to rank 0.
+
+`engine` is anything with the Engine.deflate_segments_device / inflate_segments_device signature (tests drive the host logic with a CPU
 stand-in built on the oracle; the product always passes zlibstream_b200.Engine).
 """
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -83,10 +88,12 @@ def deflate_sharded(engine, combine, local_in: torch.Tensor, seg_size: int, leve
             res.stream = gather_to[:res.total_len]
         return res
     # 2. all_gather of per-rank (compressed bytes, input bytes, adler)
-    mine = torch.tensor([out_len, n, adler], dtype=torch.int64, device=local_in.device)
+    # rank 0 decides whether the stream is gathered; the flag travels with the sizes so that every rank agrees
+    mine = torch.tensor([out_len, n, adler, 1 if gather_to is not None else 0], dtype=torch.int64, device=local_in.device)
     allv = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allv, mine, group=group)
     table = torch.stack(allv).cpu().tolist()
+    gather_on = bool(table[0][3])
     res.sizes = [int(r[0]) for r in table]
     lengths = [int(r[1]) for r in table]
     adlers = [int(r[2]) for r in table]
@@ -95,19 +102,8 @@ def deflate_sharded(engine, combine, local_in: torch.Tensor, seg_size: int, leve
     res.adler = combine_adlers(adlers, lengths, combine)
     res.total_len = sum(res.sizes) + 6
     # 4. variable-size gather to rank 0
-    if gather_to is not None or rank != 0:
-        ops = []
-        if rank == 0:
-            if gather_to is not None:
-                gather_to[:out_len].copy_(local_out[:out_len])
-                for r in range(1, world):
-                    if res.sizes[r]:
-                        ops.append(dist.P2POp(dist.irecv, gather_to[res.offsets[r]:res.offsets[r] + res.sizes[r]], r, group))
-        elif out_len and _wants_gather(gather_to, group):
-            ops.append(dist.P2POp(dist.isend, local_out[:out_len], 0, group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+    if gather_on:
+        _gather_to_rank0(rank, world, local_out, out_len, res.sizes, res.offsets, gather_to, group)
     # 5. trailer on rank 0
     if rank == 0 and gather_to is not None:
         _write_trailer(gather_to, sum(res.sizes), res.adler)
@@ -115,10 +111,102 @@ def deflate_sharded(engine, combine, local_in: torch.Tensor, seg_size: int, leve
     return res
 
 
-def _wants_gather(gather_to, group) -> bool:
-    # non-zero ranks cannot see rank 0's gather_to; by convention they pass a 1-element tensor (or anything not None)
-    # when the gather is on, None when it is off
-    return gather_to is not None
+def _gather_to_rank0(rank, world, local, local_len, sizes, offsets, gather_to, group):
+    """Variable-size gather (NCCL has no gatherv): batched isend / irecv into rank 0's buffer at the scanned offsets."""
+    ops = []
+    if rank == 0:
+        gather_to[:local_len].copy_(local[:local_len])
+        for r in range(1, world):
+            if sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, gather_to[offsets[r]:offsets[r] + sizes[r]], r, group))
+    elif local_len:
+        ops.append(dist.P2POp(dist.isend, local[:local_len], 0, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def shard_index(seg_ends: Sequence[int], header_len: int, world: int, rank: int) -> Tuple[int, int, int, int]:
+    """This rank's share of a stream's segment index: (first segment, one past the last segment, first compressed byte,
+    one past the last compressed byte).  seg_ends are the end offsets of the segments inside the stream (as written by
+    zsb_deflate_segments or found by zsb_build_segment_index).  The header_len bytes in front of segment 0 belong to the
+    slice of the rank that holds segment 0 (it passes has_header=True to inflate_sharded when header_len == 2)."""
+    b, e = shard_segments(len(seg_ends), world, rank)
+    lo = int(seg_ends[b - 1]) if b else 0
+    hi = int(seg_ends[e - 1]) if e > b else max(lo, header_len if b == 0 else lo)
+    return b, e, lo, hi
+
+
+class ShardedInflateResult:
+    __slots__ = ("local_len", "local_adler", "lengths", "offsets", "total_len", "adler", "carry", "out")
+
+    def __init__(self):
+        self.local_len = 0
+        self.local_adler = 1
+        self.lengths: List[int] = []
+        self.offsets: List[int] = []
+        self.total_len = 0
+        self.adler = 1
+        self.carry = 0
+        self.out: Optional[torch.Tensor] = None   # rank 0 only, when gathered
+
+
+def inflate_sharded(engine, combine, local_comp: torch.Tensor, local_ends: torch.Tensor, seg_size: int,
+                    local_out: torch.Tensor, has_header: bool, expect_adler: Optional[int] = None,
+                    gather_to: Optional[torch.Tensor] = None, group=None) -> ShardedInflateResult:
+    """Decodes this rank's contiguous range of segments and runs the exchange step.
+
+    local_comp = the stream's bytes [lo, hi) of shard_index (rank 0's slice starts with the 2-byte header when has_header);
+    local_ends = int64 end offsets of this rank's segments relative to local_comp; local_out receives the decoded bytes.
+    expect_adler = the stream's trailer value (every rank raises "incorrect data check" if the fold differs).
+    gather_to (rank 0; None = leave the output sharded on the GPUs) receives the whole decoded stream.
+    """
+    from .options import ZlibStreamException
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    res = ShardedInflateResult()
+    nseg = int(local_ends.numel())
+    out_len, adler = engine.inflate_segments_device(local_comp.data_ptr(), int(local_comp.numel()), local_ends.data_ptr(), nseg,
+                                                    seg_size, local_out.data_ptr(), int(local_out.numel()),
+                                                    header=has_header, trailer=False, continuation=rank > 0)
+    carry = int(engine.last_inflate_carry())
+    res.local_len, res.local_adler, res.carry = out_len, adler, carry
+    if world == 1:
+        res.lengths, res.offsets, res.total_len, res.adler = [out_len], [0], out_len, adler
+    else:
+        # (decoded bytes, adler, Q14 carry of my first segment, my last byte, rank 0's gather flag)
+        mine = torch.tensor([out_len, adler, carry, 0, 1 if gather_to is not None else 0], dtype=torch.int64, device=local_out.device)
+        if out_len:
+            mine[3] = local_out[out_len - 1]
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine, group=group)
+        table = torch.stack(allv).cpu().tolist()
+        res.lengths = [int(r[0]) for r in table]
+        adlers = [int(r[1]) for r in table]
+        carries = [int(r[2]) for r in table]
+        if any(carries[1:]):
+            # Q14: a shard that opens with a run of the byte before it takes that byte from the nearest earlier shard whose
+            # last byte is its own (a shard that is one carried run from end to end passes the byte on)
+            if rank > 0 and carry:
+                src = next((r for r in range(rank - 1, -1, -1) if res.lengths[r] > carries[r] or r == 0), 0)
+                adler = engine.inflate_fill_carry(int(table[src][3]))
+                res.local_adler = adler
+            fixed = torch.tensor([adler], dtype=torch.int64, device=local_out.device)
+            allf = [torch.empty_like(fixed) for _ in range(world)]
+            dist.all_gather(allf, fixed, group=group)
+            adlers = [int(t.item()) for t in allf]
+        res.offsets = exclusive_scan(res.lengths)
+        res.total_len = sum(res.lengths)
+        res.adler = combine_adlers(adlers, res.lengths, combine)
+        if bool(table[0][4]):
+            _gather_to_rank0(rank, world, local_out, out_len, res.lengths, res.offsets, gather_to, group)
+    if rank == 0 and gather_to is not None:
+        if world == 1:
+            gather_to[:out_len].copy_(local_out[:out_len])
+        res.out = gather_to[:res.total_len]
+    if expect_adler is not None and (res.adler & 0xFFFFFFFF) != (expect_adler & 0xFFFFFFFF):
+        raise ZlibStreamException("inflating: incorrect data check")   # Inflate.cs:335-342
+    return res
 
 
 def _write_trailer(buf: torch.Tensor, at: int, adler: int):

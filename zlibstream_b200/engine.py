@@ -169,15 +169,30 @@ class Engine:
         return out_len.value, adler.value
 
     def inflate_segments_device(self, in_ptr: int, n: int, seg_end_ptr: int, nseg: int, seg_size: int, out_ptr: int,
-                                out_cap: int, header: bool = True, trailer: bool = True):
+                                out_cap: int, header: bool = True, trailer: bool = True, continuation: bool = False):
+        """continuation: `in` is a later shard of a stream (its first segment may open with a Q14 run, see dist.py)."""
         out_len = ctypes.c_size_t(0)
         adler = ctypes.c_uint32(0)
         flags = _native.ZSB_IN_DEVICE | _native.ZSB_OUT_DEVICE | _native.ZSB_OFFSETS_DEVICE
         flags |= (0 if header else _native.ZSB_NO_HEADER) | (0 if trailer else _native.ZSB_NO_TRAILER)
+        flags |= _native.ZSB_CONTINUATION if continuation else 0
         rc = self._lib.zsb_inflate_segments(self._h, in_ptr, n, seg_end_ptr, nseg, seg_size, flags, out_ptr, out_cap,
                                             ctypes.byref(out_len), ctypes.byref(adler))
         self._check(rc, False)
         return out_len.value, adler.value
+
+    def last_inflate_carry(self) -> int:
+        """Q14: leading bytes of the last inflate call's first segment that repeat the byte before the call's input."""
+        c = ctypes.c_uint32(0)
+        self._lib.zsb_ctx_last_inflate_carry(self._h, ctypes.byref(c))
+        return c.value
+
+    def inflate_fill_carry(self, prev_byte: int) -> int:
+        """Q14: completes the device output of the last inflate call with the byte before it; returns its Adler-32."""
+        a = ctypes.c_uint32(0)
+        rc = self._lib.zsb_inflate_fill_carry(self._h, prev_byte & 0xFF, ctypes.byref(a))
+        self._check(rc, False)
+        return a.value
 
     def adler32_device(self, ptr: int, n: int, seed: int = 1) -> int:
         res = ctypes.c_uint32(0)

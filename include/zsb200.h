@@ -82,6 +82,9 @@ ZSB_API uint64_t zsb_ctx_launch_count(const zsb_ctx* ctx);
 /* Device time (ms, CUDA events on the context's stream) of the LZ77 / Huffman / inflate kernels of
  * the last call; any pointer may be NULL. */
 ZSB_API int zsb_ctx_last_kernel_ms(const zsb_ctx* ctx, float* lz77_ms, float* huffman_ms, float* inflate_ms);
+/* The same with the two level-1 LZ77 kernels apart: out[0..4] = lz77 stage, huffman stage, inflate, lz77_lists_kernel,
+ * lz77_resolve_kernel (the last two are 0 when the call did not take the two-kernel path). */
+ZSB_API int zsb_ctx_last_kernel_ms_detail(const zsb_ctx* ctx, float* out, int n);
 
 /* Upper bound of what zsb_deflate_segments can write for n input bytes. */
 ZSB_API size_t zsb_deflate_bound(size_t n, size_t seg_size);

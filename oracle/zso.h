@@ -120,6 +120,12 @@ int zso_inflate_raw(const uint8_t* in, size_t n, uint8_t* out, size_t out_cap, s
 uint32_t zso_adler32(uint32_t seed, const uint8_t* p, size_t n);                 /* Adler32.cs:270-326 */
 uint32_t zso_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);           /* zlib formula   */
 
+/* ---- timing helpers for bench.py's CPU legs (zso_bench.c): native pinned threads, no Python in the timed region -------- */
+int zso_bench_deflate_mt(const uint8_t* in, size_t n, size_t seg_size, int level, int strategy, int hash_variant, int threads,
+                         int reps, double* seconds, uint64_t* out_bytes);
+int zso_bench_inflate_mt(const uint8_t* comp, const uint64_t* seg_ends, size_t nseg, size_t first_offset, size_t seg_size,
+                         int which /* 1 system zlib, 2 oracle */, int threads, int reps, double* seconds, uint64_t* decoded);
+
 /* ---- hash (exposed for table generation checks) ------------------------------------ */
 uint32_t zso_crc32c_u32(uint32_t crc, uint32_t v);                               /* Sse42.Crc32  */
 

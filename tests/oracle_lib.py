@@ -25,7 +25,7 @@ class Counters(ctypes.Structure):
 
 
 def build():
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("zso_deflate.c", "zso_inflate.c", "zso_adler32.c", "zso.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("zso_deflate.c", "zso_inflate.c", "zso_adler32.c", "zso_bench.c", "zso.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
@@ -145,6 +145,24 @@ class Oracle:
                                   ctypes.byref(msg))
         return rc, out.raw[:n.value], ad.value, (msg.value or b"").decode(), used.value
 
+    def bench_deflate_mt(self, data, seg_size, level, strategy=0, hv=0, threads=1, reps=1):
+        """-> (seconds, compressed bytes of one pass): native pinned threads, one contiguous segment range per thread."""
+        sec = ctypes.c_double(0)
+        ob = ctypes.c_uint64(0)
+        rc = self.lib.zso_bench_deflate_mt(data, len(data), seg_size, level, strategy, hv, threads, reps, ctypes.byref(sec), ctypes.byref(ob))
+        assert rc == 0, rc
+        return sec.value, ob.value
+
+    def bench_inflate_mt(self, comp, seg_ends, first_offset, seg_size, which=1, threads=1, reps=1):
+        """-> (seconds, decoded bytes of one pass); which: 1 system zlib, 2 the oracle's inflater."""
+        ends = (ctypes.c_uint64 * len(seg_ends))(*seg_ends)
+        sec = ctypes.c_double(0)
+        dec = ctypes.c_uint64(0)
+        rc = self.lib.zso_bench_inflate_mt(comp, ends, len(seg_ends), first_offset, seg_size, which, threads, reps,
+                                           ctypes.byref(sec), ctypes.byref(dec))
+        assert rc == 0, rc
+        return sec.value, dec.value
+
     def adler32(self, data, seed=1):
         return self.lib.zso_adler32(seed, data, len(data))
 
@@ -182,6 +200,10 @@ def load():
         lib.zso_deflater_counters.argtypes = [c.c_void_p, c.POINTER(Counters)]
         lib.zso_inflate.argtypes = [c.c_char_p, c.c_size_t, c.c_void_p, c.c_size_t, c.POINTER(c.c_size_t),
                                     c.POINTER(c.c_size_t), c.POINTER(c.c_uint32), c.POINTER(c.c_char_p)]
+        lib.zso_bench_deflate_mt.argtypes = [c.c_char_p, c.c_size_t, c.c_size_t, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
+                                             c.POINTER(c.c_double), c.POINTER(c.c_uint64)]
+        lib.zso_bench_inflate_mt.argtypes = [c.c_char_p, c.POINTER(c.c_uint64), c.c_size_t, c.c_size_t, c.c_size_t, c.c_int, c.c_int,
+                                             c.c_int, c.POINTER(c.c_double), c.POINTER(c.c_uint64)]
         lib.zso_adler32.restype = c.c_uint32
         lib.zso_adler32.argtypes = [c.c_uint32, c.c_char_p, c.c_size_t]
         lib.zso_adler32_combine.restype = c.c_uint32

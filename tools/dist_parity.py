@@ -58,9 +58,7 @@ def main():
         total_len, want_adler = int(meta[0]), int(meta[1])
         stream = gather[:total_len].clone() if rank == 0 else torch.empty(total_len, dtype=torch.uint8, device=dev)
         dist.broadcast(stream, 0)
-        all_ends = [torch.empty_like(ends) for _ in range(world)] if (s1 - s0) * world == nseg else None
         # segment ends of the whole stream: every rank's local ends + its scanned offset
-        sizes = torch.tensor(res.sizes, dtype=torch.int64)
         offs = torch.tensor(res.offsets, dtype=torch.int64)
         my = (ends[:s1 - s0] + int(offs[rank])).to(torch.int64)
         cnt = torch.tensor([s1 - s0], dtype=torch.int64, device=dev)

@@ -15,7 +15,7 @@ ZSB_CONTINUATION = 0x20
 # every symbol include/zsb200.h declares
 EXPORTS = [
     "zsb_ctx_create", "zsb_ctx_destroy", "zsb_last_error", "zsb_ctx_set_stream", "zsb_ctx_get_stream",
-    "zsb_ctx_launch_count", "zsb_ctx_last_kernel_ms", "zsb_deflate_bound", "zsb_deflate_segments",
+    "zsb_ctx_launch_count", "zsb_ctx_last_kernel_ms", "zsb_ctx_last_kernel_ms_detail", "zsb_deflate_bound", "zsb_deflate_segments",
     "zsb_inflate_segments", "zsb_ctx_last_inflate_carry", "zsb_inflate_fill_carry", "zsb_build_segment_index", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
 ]
 
@@ -52,6 +52,8 @@ def load():
     lib.zsb_ctx_launch_count.restype = u64
     lib.zsb_ctx_last_kernel_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float), c.POINTER(c.c_float)]
     lib.zsb_ctx_last_kernel_ms.restype = i32
+    lib.zsb_ctx_last_kernel_ms_detail.argtypes = [vp, c.POINTER(c.c_float), i32]
+    lib.zsb_ctx_last_kernel_ms_detail.restype = i32
     lib.zsb_deflate_bound.argtypes = [sz, sz]
     lib.zsb_deflate_bound.restype = sz
     lib.zsb_deflate_segments.argtypes = [vp, vp, sz, sz, i32, i32, i32, u64, vp, c.c_uint, vp, sz, c.POINTER(sz), vp,

@@ -88,7 +88,9 @@ struct zsb_ctx {
     // timing of the last call
     std::vector<cudaEvent_t> ev;  // pairs
     std::vector<int> ev_kind;     // 0 lz77, 1 huffman, 2 inflate
-    float ms[3] = {0, 0, 0};
+    std::vector<cudaEvent_t> ev_mid;   // between the two level-1 kernels of a batch (pairs with ev[2i], ev[2i+1] of kind 0)
+    std::vector<int> ev_mid_of;        // index into ev of the pair's first event
+    float ms[5] = {0, 0, 0, 0, 0};     // 0 lz77 stage, 1 huffman stage, 2 inflate, 3 lz77_lists_kernel, 4 lz77_resolve_kernel
     bool ms_valid = true;
 };
 
@@ -133,7 +135,10 @@ void timing_begin(zsb_ctx* c)
     for (auto e : c->ev) cudaEventDestroy(e);
     c->ev.clear();
     c->ev_kind.clear();
-    c->ms[0] = c->ms[1] = c->ms[2] = 0;
+    for (auto e : c->ev_mid) cudaEventDestroy(e);
+    c->ev_mid.clear();
+    c->ev_mid_of.clear();
+    for (float& m : c->ms) m = 0;
     c->ms_valid = false;
 }
 void timing_mark(zsb_ctx* c, int kind, bool start)
@@ -150,6 +155,15 @@ void timing_collect(zsb_ctx* c)
     for (size_t i = 0; i + 1 < c->ev.size(); i += 2) {
         float m = 0;
         if (cudaEventElapsedTime(&m, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->ms[c->ev_kind[i / 2]] += m;
+    }
+    for (size_t k = 0; k < c->ev_mid.size(); k++) {
+        const size_t i = (size_t)c->ev_mid_of[k];
+        float a = 0, b = 0;
+        if (i + 1 < c->ev.size() && cudaEventElapsedTime(&a, c->ev[i], c->ev_mid[k]) == cudaSuccess &&
+            cudaEventElapsedTime(&b, c->ev_mid[k], c->ev[i + 1]) == cudaSuccess) {
+            c->ms[3] += a;
+            c->ms[4] += b;
+        }
     }
     c->ms_valid = true;
 }
@@ -403,6 +417,16 @@ int zsb_inflate_fill_carry(zsb_ctx* ctx, uint8_t prev_byte, uint32_t* adler)
     return ZSB_OK;
 }
 
+int zsb_ctx_last_kernel_ms_detail(const zsb_ctx* cctx, float* out, int n)
+{
+    zsb_ctx* ctx = const_cast<zsb_ctx*>(cctx);
+    if (!ctx || !out) return ZSB_STREAM_ERROR;
+    cudaStreamSynchronize(ctx->stream);
+    timing_collect(ctx);
+    for (int i = 0; i < n; i++) out[i] = i < 5 ? ctx->ms[i] : 0.f;
+    return ZSB_OK;
+}
+
 size_t zsb_deflate_bound(size_t n, size_t seg_size)
 {
     const size_t segs = seg_size ? (n + seg_size - 1) / seg_size : 1;
@@ -575,6 +599,13 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         L.lists = use_lists ? ctx->lists.as<uint4>() : nullptr;
         CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
         timing_mark(ctx, 0, true);
+        if (use_lists) {   // an event between the two level-1 kernels: their times are reported apart
+            cudaEvent_t mid;
+            CU(cudaEventCreate(&mid));
+            ctx->ev_mid.push_back(mid);
+            ctx->ev_mid_of.push_back((int)ctx->ev.size() - 1);
+            L.ev_mid = mid;
+        }
         CU(launch_lz77(L, ctx->num_sms, st));
         timing_mark(ctx, 0, false);
         ctx->launches++;

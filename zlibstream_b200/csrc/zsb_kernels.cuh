@@ -27,6 +27,7 @@ struct Lz77Params {
     // level 1, two-kernel path (zsb_lz77_lists.cu + zsb_lz77_resolve.cu): 32-byte candidate records, [nseg][seg_size] x 2 uint4;
     // nullptr = not available (the batch parser of zsb_lz77.cu runs instead).  work_counter then points to three counters.
     uint4* lists = nullptr;
+    cudaEvent_t ev_mid = nullptr;   // optional: recorded between the two kernels
 };
 constexpr int LZ_LIST_K = 10;          // candidates per record
 bool lz77_lists_applies(const Lz77Params& P);

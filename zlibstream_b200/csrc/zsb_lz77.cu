@@ -1386,6 +1386,7 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
             F.nseg = nfull;
             cudaError_t e = launch_lz77_lists(F, num_sms, stream);
             if (e != cudaSuccess) return e;
+            if (P.ev_mid) cudaEventRecord(P.ev_mid, stream);
             e = launch_lz77_resolve(F, num_sms, stream);
             if (e != cudaSuccess) return e;
         }

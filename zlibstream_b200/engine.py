@@ -76,7 +76,9 @@ class Engine:
     def last_kernel_ms(self):
         a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
         self._lib.zsb_ctx_last_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-        return {"lz77": a.value, "huffman": b.value, "inflate": c.value}
+        d = (ctypes.c_float * 5)()
+        self._lib.zsb_ctx_last_kernel_ms_detail(self._h, d, 5)
+        return {"lz77": a.value, "huffman": b.value, "inflate": c.value, "lz77_lists": d[3], "lz77_resolve": d[4]}
 
     def deflate_bound(self, n: int, seg_size: int) -> int:
         return int(self._lib.zsb_deflate_bound(n, seg_size))

@@ -5,7 +5,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-LIB = os.path.join(ORACLE_DIR, "libzso.so")
+LIB = os.environ.get("ZSO_LIB") or os.path.join(ORACLE_DIR, "libzso.so")   # ZSO_LIB: the ASan build (make -C oracle asan)
 
 _lib = None
 
@@ -25,6 +25,8 @@ class Counters(ctypes.Structure):
 
 
 def build():
+    if os.environ.get("ZSO_LIB"):
+        return LIB
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("zso_deflate.c", "zso_inflate.c", "zso_adler32.c", "zso_bench.c", "zso.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB

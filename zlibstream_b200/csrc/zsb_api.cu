@@ -178,17 +178,20 @@ __global__ void finalize_stream_kernel(uint8_t* out, size_t out_cap, uint64_t* t
         out[0] = (uint8_t)(header >> 8);
         out[1] = (uint8_t)header;
     }
-    if (write_trailer) {
+    if (write_trailer) {   // 1: `03 00` + Adler-32; 2: the final block is already in the stream (one-piece stream), Adler-32 only
         uint64_t o = *total_out;
-        if (o + 6 > out_cap) { *status = ZSB_BUF_ERROR; *total_out = o + 6; return; }
+        const uint64_t need = write_trailer == 2 ? 4 : 6;
+        if (o + need > out_cap) { *status = ZSB_BUF_ERROR; *total_out = o + need; return; }
         const uint32_t a = *adler;
-        out[o] = 0x03;
-        out[o + 1] = 0x00;
-        out[o + 2] = (uint8_t)(a >> 24);
-        out[o + 3] = (uint8_t)(a >> 16);
-        out[o + 4] = (uint8_t)(a >> 8);
-        out[o + 5] = (uint8_t)a;
-        *total_out = o + 6;
+        if (write_trailer != 2) {
+            out[o++] = 0x03;
+            out[o++] = 0x00;
+        }
+        out[o] = (uint8_t)(a >> 24);
+        out[o + 1] = (uint8_t)(a >> 16);
+        out[o + 2] = (uint8_t)(a >> 8);
+        out[o + 3] = (uint8_t)a;
+        *total_out = o + 4;
     }
 }
 
@@ -448,6 +451,14 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     if (strategy < 0 || strategy > ZSB_FIXED) return fail(ctx, ZSB_STREAM_ERROR, "strategy");
     if (hash_variant != ZSB_HASH_CRC32C && hash_variant != ZSB_HASH_MUL) return fail(ctx, ZSB_STREAM_ERROR, "hash_variant");
     if ((n && !in) || !out) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
+    // One Write with FlushMode.NoFlush + Dispose (the reference's benchmark call pattern, DeflateCorpusBenchmark.cs:86-99): the
+    // whole input is one segment of the stream's first kind whose last block carries BFINAL; no flush marker, no `03 00`.
+    const bool single = (flags & ZSB_SINGLE_STREAM) != 0;
+    if (single) {
+        if (n > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream holds at most 64 MiB on the device path");
+        if (first_segment_index != 0) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream starts at segment 0");
+        seg_size = n <= 65536 ? 65536 : (n + 32767) & ~(size_t)32767;
+    }
     if (seg_size < 65536 || (seg_size & 32767) != 0 || seg_size > (64u << 20))
         return fail(ctx, ZSB_STREAM_ERROR, "seg_size must be a multiple of 32768, >= 65536 and <= 64 MiB");
     if (level == 0 && strategy != ZSB_RLE)
@@ -519,7 +530,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         probe.fn = strategy == ZSB_RLE ? FN_RLE : cfg.fn;
         probe.stats = ctx->lz_stats;
         const char* l1 = getenv("ZSB_L1_KERNEL");
-        use_lists = lz77_lists_applies(probe) && !(l1 && strcmp(l1, "batch") == 0);
+        use_lists = lz77_lists_applies(probe) && !(l1 && strcmp(l1, "batch") == 0) && !single;
     }
     const size_t list_bytes_per_seg = use_lists ? lz77_lists_bytes_per_segment((uint32_t)seg_size) : 0;
     const size_t per_seg = sym_bytes_per_seg + list_bytes_per_seg + max_blocks * (sizeof(BlockRec) + sizeof(BlockCodesDev)) + sizeof(uint32_t) + sizeof(SegLayout);
@@ -630,6 +641,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         H.out = d_out;
         H.out_cap = out_cap;
         H.status = d_status;
+        H.finish_mode = single ? 1 : 0;
         timing_mark(ctx, 1, true);
         CU(launch_block_trees(H, st));
         CU(launch_layout(H, st));
@@ -661,7 +673,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     header |= level_flags << 6;
     header += 31 - (header % 31);
     finalize_stream_kernel<<<1, 1, 0, st>>>(d_out, out_cap, d_total, d_adler, write_header ? 1 : 0, header,
-                                            write_trailer ? 1 : 0, d_status);
+                                            write_trailer ? ((single && nseg) ? 2 : 1) : 0, d_status);
     CU(cudaGetLastError());
     ctx->launches++;
 
@@ -693,12 +705,26 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     ctx->err.clear();
     if (out_len) *out_len = 0;
     if (!in || (!out && out_cap)) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
-    if (seg_size == 0 || seg_size > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "seg_size");
+    const bool single = (flags & ZSB_SINGLE_STREAM) != 0;
+    const bool has_header = !(flags & ZSB_NO_HEADER), has_trailer = !(flags & ZSB_NO_TRAILER);
+    // a one-piece stream (written without full flushes) is one segment that ends with its final block; its trailer is the
+    // Adler-32 alone (Inflate.cs:286-342)
+    const size_t trailer_len = has_trailer ? (single ? 4u : 6u) : 0u;
+    uint64_t single_end = 0;
+    if (single) {
+        if (n < (has_header ? 2u : 0u) + trailer_len) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+        if (out_cap > 0xF0000000ull) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream may decode to at most 0xF0000000 bytes");
+        single_end = n - trailer_len;
+        seg_end_offsets = &single_end;
+        nseg = 1;
+        seg_size = out_cap ? out_cap : 1;
+        flags &= ~ZSB_OFFSETS_DEVICE;
+    }
+    if (seg_size == 0 || (!single && seg_size > (64u << 20))) return fail(ctx, ZSB_STREAM_ERROR, "seg_size");
     if (seg_end_offsets && nseg > 0xFFFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "too many segments");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     timing_begin(ctx);
-    const bool has_header = !(flags & ZSB_NO_HEADER), has_trailer = !(flags & ZSB_NO_TRAILER);
 
     // ---- header checks on the host (Inflate.cs:120-178) need the first two bytes ----
     uint8_t hdr[2] = {0, 0};
@@ -722,8 +748,8 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     std::vector<uint64_t> host_ends;
     if (!seg_end_offsets) {
         // no side-car: find the segments by their full-flush markers
-        if (n < (has_header ? 2u : 0u) + (has_trailer ? 6u : 0u)) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
-        int rc = build_segment_index(ctx, d_in, n, has_header ? 2 : 0, n - (has_trailer ? 6 : 0), seg_size, host_ends);
+        if (n < (has_header ? 2u : 0u) + trailer_len) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+        int rc = build_segment_index(ctx, d_in, n, has_header ? 2 : 0, n - trailer_len, seg_size, host_ends);
         if (rc != ZSB_OK) return rc;
         seg_end_offsets = host_ends.data();
         nseg = host_ends.size();
@@ -743,7 +769,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
             CU(cudaStreamSynchronize(st));
         } else last_end = seg_end_offsets[nseg - 1];
     }
-    if (last_end + (has_trailer ? 6 : 0) > n) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+    if (last_end + trailer_len > n) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
 
     uint8_t* d_out = reinterpret_cast<uint8_t*>(out);
     if (!(flags & ZSB_OUT_DEVICE)) {
@@ -807,7 +833,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         CU(cudaMemcpyAsync(status.data(), ctx->inf_status.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(lens.data(), ctx->inf_len.p, nseg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
-    if (has_trailer) CU(cudaMemcpyAsync(trailer, d_in + last_end, 6, cudaMemcpyDeviceToHost, st));
+    if (has_trailer) CU(cudaMemcpyAsync(trailer, d_in + last_end, trailer_len, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     size_t produced = 0;
     for (size_t k = 0; k < nseg; k++) {
@@ -843,9 +869,10 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     CU(cudaStreamSynchronize(st));
     if (adler) *adler = got_adler;
     if (has_trailer) {
-        // final block must be the empty static block `03 00` (Q12) followed by the big-endian Adler-32
-        if (trailer[0] != 0x03 || trailer[1] != 0x00) return fail(ctx, ZSB_DATA_ERROR, "invalid block type");
-        const uint32_t want = ((uint32_t)trailer[2] << 24) | ((uint32_t)trailer[3] << 16) | ((uint32_t)trailer[4] << 8) | trailer[5];
+        // segmented: the final block must be the empty static block `03 00` (Q12); then the big-endian Adler-32
+        const uint8_t* tw = single ? trailer : trailer + 2;
+        if (!single && (trailer[0] != 0x03 || trailer[1] != 0x00)) return fail(ctx, ZSB_DATA_ERROR, "invalid block type");
+        const uint32_t want = ((uint32_t)tw[0] << 24) | ((uint32_t)tw[1] << 16) | ((uint32_t)tw[2] << 8) | tw[3];
         if (want != got_adler) return fail(ctx, ZSB_DATA_ERROR, "incorrect data check");  // Inflate.cs:335-342
     }
     if (!(flags & ZSB_OUT_DEVICE) && produced) {

@@ -423,6 +423,12 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(HuffParams P)
             for (int i = 0; i < kTailWords; i++) t.w[i] = 0;
             t.nbits = 0;
             const uint64_t tail_start = bitpos;
+            if (P.finish_mode) {
+                // NoFlush + Finish (Deflate.cs:616-635): the last block was sent with BFINAL and Bi_windup pads to a byte; nothing
+                // is flushed in between, so the 512-byte chunk arithmetic never adds a block
+                bitpos = (bitpos + 7) & ~7ull;
+                drained = false;
+            }
             // `do { block with the remaining symbols; step } while (drained)`: the first one is block nb-1
             while (drained) {
                 t.put(0x2u, 3);  // BFINAL=0, static
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(HuffParams P)
                 bitpos += 10;
                 drained = dr.step(bitpos);
             }
-            for (;;) {
+            for (; !P.finish_mode;) {
                 // Tr_stored_block(0, 0, false): 3 type bits, Bi_windup, LEN=0000 NLEN=FFFF
                 t.put(0u, 3);
                 bitpos += 3;
@@ -587,7 +593,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(HuffParams P)
         const BlockCodesDev& codes = P.codes[(size_t)seg * P.max_blocks + b];
         // block type bits: BFINAL = 0 (Trees.cs:755-756)
         if (pk.stage_bits_free() < 4096) pk.flush(false);
-        if (tid == 0) pk.or_bits(seg_bit0 + r.bit_offset, (uint64_t)(r.type << 1), 3);
+        if (tid == 0) pk.or_bits(seg_bit0 + r.bit_offset, (uint64_t)(r.type << 1) | (uint64_t)((P.finish_mode && b + 1 == nb) ? 1u : 0u), 3);
         pk.bitpos = seg_bit0 + r.bit_offset + 3;
         if (r.type == BT_STORED) {
             // Copy_block (Deflate.cs:710-722): byte align, LEN, NLEN, raw bytes

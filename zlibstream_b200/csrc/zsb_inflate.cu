@@ -211,8 +211,10 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
             br.limit = room > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)room;
         }
 
-        // blocks until the segment's compressed bytes are used up (it ends with the full-flush marker)
-        while (err == IE_OK) {
+        // blocks until the segment's compressed bytes are used up (it ends with the full-flush marker) or, in a one-piece
+        // stream, until its final block is done (Inflate.cs:286-300)
+        bool final_seen = false;
+        while (err == IE_OK && !final_seen) {
             int hdr = -1;
             if (lane == 0) {
                 const uint32_t used = br.byte_pos();
@@ -224,7 +226,8 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_segments_kernel(InflatePa
             hdr = __shfl_sync(gmask, hdr, 0, GW);
             if (hdr == -2) break;
             if (hdr == -3) { err = IE_TRUNCATED; break; }
-            const int type = hdr >> 1;   // BFINAL is ignored inside a segment: the stream's final block is the caller's
+            const int type = hdr >> 1;
+            final_seen = (hdr & 1) != 0;   // segments of a full-flush stream never hold one: the stream's `03 00` lies outside them
             if (type == 0) {
                 // stored (InflateBlocks.cs:251-364)
                 int len = -1;

@@ -113,6 +113,7 @@ struct Lane {
     uint32_t found;        // count-only: offset just past the full-flush marker that ended the piece, 0 = none yet
     uint32_t carry;        // Q14: leading bytes that repeat the previous segment's last byte (Rle streams only)
     uint32_t carry_ok;     // this segment is not the stream's first: it may open with such a run
+    uint32_t final_seen;   // a block with BFINAL has been entered: the segment (a one-piece stream) ends with it
     uint64_t bl_lens;      // 19 x 3 bits
 };
 
@@ -335,6 +336,10 @@ ZL_HD int bl_order(int i)   // InflateBlocks.cs:21 `border`
 // Block header (InflateBlocks.cs:190-250, 366-470)
 ZL_HD void block_step(Lane& L)
 {
+    if (L.final_seen && !L.count) {   // the final block of a one-piece stream (Inflate.cs:286-300): nothing follows but padding
+        L.st = S_FINISH;
+        return;
+    }
     const uint32_t used = byte_pos(L);
     if (L.nbits < 0 || used > L.end) return lane_fail(L, IE_TRUNCATED);   // ran past the segment's bytes
     if (used == L.end) {                                                  // clean end, after the byte-aligned full-flush marker
@@ -346,7 +351,8 @@ ZL_HD void block_step(Lane& L)
     if (L.nbits < 3) return lane_fail(L, IE_TRUNCATED);
     const uint32_t hdr = peek(L, 3);
     drop(L, 3);
-    const uint32_t type = hdr >> 1;   // BFINAL is ignored inside a segment: the stream's final block is the caller's
+    const uint32_t type = hdr >> 1;
+    L.final_seen = hdr & 1u;          // segments of a full-flush stream never hold one: the stream's `03 00` lies outside them
     if (type == 0) {
         drop(L, L.nbits & 7);
         refill(L);
@@ -631,6 +637,7 @@ ZL_HD void begin_segment(Lane& L, const InflateParams& P, uint32_t seg)
 {
     L.seg = seg;
     L.carry_ok = (seg > 0 || P.continuation) ? 1u : 0u;
+    L.final_seen = 0;
     L.err = IE_OK;
     L.st = S_BLOCK;
     L.pos = 0;

@@ -78,6 +78,7 @@ struct HuffParams {
     uint8_t* out;
     size_t out_cap;
     int* status;              // device int: set to ZSB_BUF_ERROR if out_cap is too small
+    int finish_mode = 0;      // 1: one Write with FlushMode.NoFlush, then Finish: the last block carries BFINAL, no flush marker
 };
 cudaError_t launch_block_trees(const HuffParams& P, cudaStream_t stream);
 cudaError_t launch_layout(const HuffParams& P, cudaStream_t stream);

@@ -131,6 +131,33 @@ class Engine:
         del keep
         return out.raw[:out_len.value], adler.value
 
+    def deflate_stream(self, data, level: int, strategy: int = 0, hash_variant: int = HashVariant.Crc32C):
+        """One Write with FlushMode.NoFlush + Dispose (the reference's benchmark call pattern, DeflateCorpusBenchmark.cs:86-99):
+        a one-piece zlib stream, at most 64 MiB of input.  Returns (stream bytes, adler32 of data)."""
+        addr, n, keep = _addr(data)
+        cap = self.deflate_bound(n, 65536) + 64
+        out = ctypes.create_string_buffer(cap)
+        out_len = ctypes.c_size_t(0)
+        adler = ctypes.c_uint32(0)
+        rc = self._lib.zsb_deflate_segments(self._h, addr, n, 0, int(level), int(strategy), int(hash_variant), 0, None,
+                                            _native.ZSB_SINGLE_STREAM, out, cap, ctypes.byref(out_len), None, ctypes.byref(adler))
+        self._check(rc, True)
+        del keep
+        return out.raw[:out_len.value], adler.value
+
+    def inflate_stream(self, comp, out_size: int):
+        """Decodes a one-piece zlib stream (any conforming deflater's, e.g. the reference's with FlushMode.NoFlush).
+        Returns (decoded bytes, adler32); raises "incorrect data check" if the trailer does not match."""
+        addr, n, keep = _addr(comp)
+        out = ctypes.create_string_buffer(max(out_size, 1))
+        out_len = ctypes.c_size_t(0)
+        adler = ctypes.c_uint32(0)
+        rc = self._lib.zsb_inflate_segments(self._h, addr, n, None, 0, 0, _native.ZSB_SINGLE_STREAM, out, out_size,
+                                            ctypes.byref(out_len), ctypes.byref(adler))
+        self._check(rc, False)
+        del keep
+        return out.raw[:out_len.value], adler.value
+
     def build_segment_index(self, comp, seg_size: int, header: bool = True, trailer: bool = True):
         """Segment index of a full-flush-segmented stream without a side-car (zsb_build_segment_index).
         Returns ([segment end offsets], uncompressed size)."""

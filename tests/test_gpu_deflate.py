@@ -32,6 +32,28 @@ def test_golden_segmented_vectors(engine, corpus, key):
     assert hashlib.sha256(",".join(map(str, ends)).encode()).hexdigest() == g["ends_sha256"]
 
 
+@pytest.mark.parametrize("n", [65536, 65536 + 32505, 65536 + 32506, 3 * 65536 + 32767, 5 * 65536, 2 * 262144 + 40000, 131072 + 1])
+@pytest.mark.parametrize("ss", [65536, 262144])
+def test_level0_stored_blocks(engine, oracle, n, ss):
+    """SURVEY 8(f)-3, DeflateStored (Deflate.Stored.cs:24-84): 32 KiB stored blocks, the empty stored block the end-of-input
+    flush leaves behind a multiple of 32 KiB or a tail >= w_size - MIN_LOOKAHEAD, empty STORED blocks where Q10 repeats."""
+    data = corpus_data.text_like(n, seed=n % 97)
+    want, want_ends, want_adler = oracle.deflate_segments(data, ss, 0, 0)
+    got, ends, adler = engine.deflate_segments(data, ss, 0, 0)
+    assert got == want and ends == want_ends and adler == want_adler
+    assert zlib.decompress(got) == data
+    dec, ad = engine.inflate_segments(got, ends, ss, len(data))
+    assert dec == data and ad == adler
+    # one Write, NoFlush, Dispose at level 0
+    one, _ = engine.deflate_stream(data, 0)
+    assert one == oracle.deflate_oneshot(data, 0)[0]
+    # Filtered / HuffmanOnly / Fixed do not change level 0 (Rle would override the level's function, Q13: not built at level 0)
+    for strategy in (1, 2, 4):
+        assert engine.deflate_segments(data, ss, 0, strategy)[0] == oracle.deflate_segments(data, ss, 0, strategy)[0]
+    with pytest.raises(Exception, match="not implemented"):
+        engine.deflate_segments(data, ss, 0, 3)
+
+
 @pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7, 8, 9, -1])
 def test_every_level_matches_oracle(engine, oracle, corpus, level):
     data = corpus["lcet10.txt"] + corpus["sum"] + corpus["ptt5"][:200000]

@@ -178,14 +178,21 @@ __global__ void finalize_stream_kernel(uint8_t* out, size_t out_cap, uint64_t* t
         out[0] = (uint8_t)(header >> 8);
         out[1] = (uint8_t)header;
     }
-    if (write_trailer) {   // 1: `03 00` + Adler-32; 2: the final block is already in the stream (one-piece stream), Adler-32 only
+    if (write_trailer) {   // 1: `03 00` + Adler-32; 2: the final block is already in the stream (one-piece stream), Adler-32 only;
+                           // 3: level 0, the final block is an empty STORED block `01 00 00 FF FF` (Deflate.Stored.cs:80 with eof)
         uint64_t o = *total_out;
-        const uint64_t need = write_trailer == 2 ? 4 : 6;
+        const uint64_t need = write_trailer == 2 ? 4 : (write_trailer == 3 ? 9 : 6);
         if (o + need > out_cap) { *status = ZSB_BUF_ERROR; *total_out = o + need; return; }
         const uint32_t a = *adler;
-        if (write_trailer != 2) {
+        if (write_trailer == 1) {
             out[o++] = 0x03;
             out[o++] = 0x00;
+        } else if (write_trailer == 3) {
+            out[o++] = 0x01;
+            out[o++] = 0x00;
+            out[o++] = 0x00;
+            out[o++] = 0xFF;
+            out[o++] = 0xFF;
         }
         out[o] = (uint8_t)(a >> 24);
         out[o + 1] = (uint8_t)(a >> 16);
@@ -461,8 +468,11 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     }
     if (seg_size < 65536 || (seg_size & 32767) != 0 || seg_size > (64u << 20))
         return fail(ctx, ZSB_STREAM_ERROR, "seg_size must be a multiple of 32768, >= 65536 and <= 64 MiB");
-    if (level == 0 && strategy != ZSB_RLE)
-        return fail(ctx, ZSB_STREAM_ERROR, "level 0 (stored) is not implemented on the device path");
+    // Rle overrides the level's function even at level 0 (Q13), where memLevel 7 makes blocks end at 8191 symbols
+    // (Deflate.cs:19-20,246-249): that combination is not built.
+    if (level == 0 && strategy == ZSB_RLE)
+        return fail(ctx, ZSB_STREAM_ERROR, "level 0 with the Rle strategy is not implemented on the device path");
+    const bool level0 = level == 0;   // DeflateStored
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     timing_begin(ctx);
@@ -642,6 +652,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         H.out_cap = out_cap;
         H.status = d_status;
         H.finish_mode = single ? 1 : 0;
+        H.level0 = level0 ? 1 : 0;
         timing_mark(ctx, 1, true);
         CU(launch_block_trees(H, st));
         CU(launch_layout(H, st));
@@ -664,7 +675,12 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         }
     }
     // ---- Adler-32 of the whole input, header, trailer ----
-    CU(launch_adler_fold(ctx->seg_adler.as<uint2>(), (uint32_t)nseg, (uint32_t)seg_size, n, 1u, d_adler, st));
+    if (level0) {   // no LZ77 kernel has read the input: checksum it here (per 64 KiB chunk, then the same fold)
+        const size_t achunks = (n + kAdlerChunk - 1) / kAdlerChunk;
+        CU(ctx->seg_adler.reserve((achunks ? achunks : 1) * sizeof(uint2)));
+        CU(launch_adler32(d_in, n, 1u, ctx->seg_adler.as<uint2>(), (uint32_t)(achunks ? achunks : 1), d_adler, st));
+        ctx->launches++;
+    } else CU(launch_adler_fold(ctx->seg_adler.as<uint2>(), (uint32_t)nseg, (uint32_t)seg_size, n, 1u, d_adler, st));
     ctx->launches++;
     // Deflate.cs:466-480 (Q11): old-zlib FLEVEL, no strategy adjustment
     uint32_t header = (8u + ((15u - 8u) << 4)) << 8;
@@ -673,7 +689,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     header |= level_flags << 6;
     header += 31 - (header % 31);
     finalize_stream_kernel<<<1, 1, 0, st>>>(d_out, out_cap, d_total, d_adler, write_header ? 1 : 0, header,
-                                            write_trailer ? ((single && nseg) ? 2 : 1) : 0, d_status);
+                                            write_trailer ? ((single && nseg) ? 2 : (level0 ? 3 : 1)) : 0, d_status);
     CU(cudaGetLastError());
     ctx->launches++;
 
@@ -709,7 +725,16 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     const bool has_header = !(flags & ZSB_NO_HEADER), has_trailer = !(flags & ZSB_NO_TRAILER);
     // a one-piece stream (written without full flushes) is one segment that ends with its final block; its trailer is the
     // Adler-32 alone (Inflate.cs:286-342)
-    const size_t trailer_len = has_trailer ? (single ? 4u : 6u) : 0u;
+    size_t trailer_len = has_trailer ? (single ? 4u : 6u) : 0u;
+    if (has_trailer && !single && n >= 9) {
+        // the final block Finish appends: the empty static block `03 00` (Q12) or, for a level-0 stream, the empty STORED block
+        // `01 00 00 FF FF` (Deflate.Stored.cs:80 with eof) -- 6 or 9 bytes with the Adler-32
+        uint8_t tail9[9];
+        if (flags & ZSB_IN_DEVICE) CU(cudaMemcpy(tail9, reinterpret_cast<const uint8_t*>(in) + n - 9, 9, cudaMemcpyDeviceToHost));
+        else memcpy(tail9, reinterpret_cast<const uint8_t*>(in) + n - 9, 9);
+        static const uint8_t kStoredFinal[5] = {0x01, 0x00, 0x00, 0xFF, 0xFF};
+        if (!(tail9[3] == 0x03 && tail9[4] == 0x00) && memcmp(tail9, kStoredFinal, 5) == 0) trailer_len = 9;
+    }
     uint64_t single_end = 0;
     if (single) {
         if (n < (has_header ? 2u : 0u) + trailer_len) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
@@ -826,7 +851,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     std::vector<int> status(nseg);
     std::vector<uint32_t> lens(nseg);
     uint32_t got_adler = 1;
-    uint8_t trailer[6] = {0};
+    uint8_t trailer[9] = {0};
     unsigned int carry_flag = 0;
     CU(cudaMemcpyAsync(&carry_flag, d_carry_flag, sizeof carry_flag, cudaMemcpyDeviceToHost, st));
     if (nseg) {
@@ -870,8 +895,8 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     if (adler) *adler = got_adler;
     if (has_trailer) {
         // segmented: the final block must be the empty static block `03 00` (Q12); then the big-endian Adler-32
-        const uint8_t* tw = single ? trailer : trailer + 2;
-        if (!single && (trailer[0] != 0x03 || trailer[1] != 0x00)) return fail(ctx, ZSB_DATA_ERROR, "invalid block type");
+        const uint8_t* tw = trailer + (trailer_len - 4);
+        if (!single && trailer_len == 6 && (trailer[0] != 0x03 || trailer[1] != 0x00)) return fail(ctx, ZSB_DATA_ERROR, "invalid block type");
         const uint32_t want = ((uint32_t)tw[0] << 24) | ((uint32_t)tw[1] << 16) | ((uint32_t)tw[2] << 8) | tw[3];
         if (want != got_adler) return fail(ctx, ZSB_DATA_ERROR, "incorrect data check");  // Inflate.cs:335-342
     }

@@ -256,6 +256,14 @@ __global__ void __launch_bounds__(BT_THREADS) block_trees_kernel(HuffParams P)
     const uint32_t seg = blockIdx.x / P.max_blocks, blk = blockIdx.x % P.max_blocks;
     if (seg >= P.nseg || blk >= P.nblocks[seg]) return;
     BlockRec& rec = P.blocks[(size_t)seg * P.max_blocks + blk];
+    if (P.level0) {   // Tr_flush_block with level == 0 (Trees.cs:586-594): opt_lenb = static_lenb = stored_len + 5, so stored wins
+        if (tid == 0) {
+            rec.type = BT_STORED;
+            rec.hdr_bits = 0;
+            rec.body_bits = 0;
+        }
+        return;
+    }
     const uint32_t* sym = P.sym + (size_t)seg * P.sym_stride + rec.sym_begin;
     const int nsym = (int)rec.sym_count;
 
@@ -429,11 +437,25 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(HuffParams P)
                 bitpos = (bitpos + 7) & ~7ull;
                 drained = false;
             }
+            // the block a repeated flush finds nothing to put into: empty static (3 + 7 bits), or at level 0 empty stored
+            auto empty_block = [&]() {
+                if (P.level0) {
+                    t.put(0u, 3);
+                    bitpos += 3;
+                    const uint32_t pad0 = (uint32_t)((8 - (bitpos & 7)) & 7);
+                    if (pad0) t.put(0u, (int)pad0);
+                    bitpos += pad0;
+                    t.put(0xFFFF0000u, 32);
+                    bitpos += 32;
+                } else {
+                    t.put(0x2u, 3);  // BFINAL=0, static
+                    t.put(0u, 7);    // END_BLOCK of the fixed tree
+                    bitpos += 10;
+                }
+            };
             // `do { block with the remaining symbols; step } while (drained)`: the first one is block nb-1
             while (drained) {
-                t.put(0x2u, 3);  // BFINAL=0, static
-                t.put(0u, 7);    // END_BLOCK of the fixed tree
-                bitpos += 10;
+                empty_block();
                 drained = dr.step(bitpos);
             }
             for (; !P.finish_mode;) {
@@ -448,9 +470,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(HuffParams P)
                 drained = dr.step(bitpos);
                 if (!drained) break;
                 do {
-                    t.put(0x2u, 3);
-                    t.put(0u, 7);
-                    bitpos += 10;
+                    empty_block();
                     drained = dr.step(bitpos);
                 } while (drained);
             }

@@ -39,6 +39,8 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream);
 // HuffmanOnly and Rle need no hash chains: zsb_symbolize.cu produces their symbols, blocks and Adler sums in parallel.
 bool symbolize_applies(const Lz77Params& P);
 cudaError_t launch_symbolize(const Lz77Params& P, int num_sms, cudaStream_t stream);
+// Level 0 (DeflateStored, Deflate.Stored.cs:24-84): block records only, no symbols, no Adler sums (the caller checksums the input).
+cudaError_t launch_stored_blocks(const Lz77Params& P, cudaStream_t stream);
 
 // ---- Huffman stage (zsb_huffman.cu) --------------------------------------------------------------
 constexpr int kHdrWords = 80;   // dynamic tree description: <= 14 + 57 + 316 * 7 bits
@@ -78,6 +80,7 @@ struct HuffParams {
     uint8_t* out;
     size_t out_cap;
     int* status;              // device int: set to ZSB_BUF_ERROR if out_cap is too small
+    int level0 = 0;           // level 0: every block is stored (Trees.cs:586-594 with level == 0), also the empty ones of Q10
     int finish_mode = 0;      // 1: one Write with FlushMode.NoFlush, then Finish: the last block carries BFINAL, no flush marker
 };
 cudaError_t launch_block_trees(const HuffParams& P, cudaStream_t stream);

@@ -1375,6 +1375,7 @@ static cudaError_t launch_lz77_classic(const Lz77Params& P, int num_sms, cudaStr
 cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
 {
     // ZSB_NO_SYMBOLIZE=1 keeps HuffmanOnly / Rle on the serial path below (A/B measurements, parity cross-checks)
+    if (P.fn == FN_STORED) return launch_stored_blocks(P, stream);
     static const bool no_symbolize = getenv("ZSB_NO_SYMBOLIZE") != nullptr;
     if (!no_symbolize && !P.stats && symbolize_applies(P)) return launch_symbolize(P, num_sms, stream);
     // ZSB_L1_KERNEL=batch keeps level 1 on the batch parser (A/B measurements, parity cross-checks); read per call

@@ -416,4 +416,70 @@ cudaError_t launch_symbolize(const Lz77Params& P, int num_sms, cudaStream_t stre
     return cudaGetLastError();
 }
 
+// ---- level 0 (DeflateStored, Deflate.Stored.cs:24-84) -----------------------------------------------------------------------
+// One thread per segment replays the loop's arithmetic: Fill_window's refill / slide schedule (Deflate.cs:967-1019; level 0
+// calls it when lookahead <= 1) and the two flush rules -- a block is cut at max_block_size = pending buffer - 5 = 32763
+// bytes (memLevel is 7 at level 0, Deflate.cs:19-20,246-249, so the pending buffer is 32 KiB) and whenever w_size -
+// MIN_LOOKAHEAD bytes are waiting (:69-76); the end-of-input flush (:80) closes whatever is left, possibly nothing.
+__global__ void __launch_bounds__(256) stored_blocks_kernel(Lz77Params P)
+{
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= P.nseg) return;
+    const size_t off = (size_t)seg * P.seg_size;
+    const int len = (int)((P.n - off) < (size_t)P.seg_size ? (P.n - off) : (size_t)P.seg_size);
+    const bool first = (P.first_seg_index + (uint64_t)seg) == 0;
+    BlockRec* b = P.blocks + (size_t)seg * P.max_blocks;
+    constexpr int MAX_BLOCK = 32768 - 5;
+    uint32_t nb = 0;
+    int str_start = first ? 0 : W_SIZE, block_start = str_start, lookahead = 0, avail = len;
+    int base = first ? 0 : -W_SIZE;   // segment offset of window index 0
+    auto flush = [&]() {
+        if (nb < P.max_blocks) {
+            BlockRec r{};
+            r.in_begin = (uint32_t)(block_start + base);
+            r.in_len = (uint32_t)(str_start - block_start);
+            r.buf_valid = block_start >= 0;
+            b[nb] = r;
+        }
+        nb++;
+        block_start = str_start;
+    };
+    for (;;) {
+        if (lookahead <= 1) {
+            do {   // Fill_window
+                int more = WINDOW_SIZE - lookahead - str_start;
+                if (str_start >= WINDOW_SIZE - MIN_LOOKAHEAD) {
+                    str_start -= W_SIZE;
+                    block_start -= W_SIZE;
+                    base += W_SIZE;
+                    more += W_SIZE;
+                }
+                if (avail == 0) break;
+                const int n = avail < more ? avail : more;
+                avail -= n;
+                lookahead += n;
+            } while (lookahead < MIN_LOOKAHEAD && avail != 0);
+            if (lookahead == 0) break;
+        }
+        str_start += lookahead;
+        lookahead = 0;
+        const int max_start = block_start + MAX_BLOCK;
+        if (str_start == 0 || str_start >= max_start) {
+            lookahead = str_start - max_start;
+            str_start = max_start;
+            flush();
+        }
+        if (str_start - block_start >= W_SIZE - MIN_LOOKAHEAD) flush();
+    }
+    flush();
+    P.nblocks[seg] = nb;
+}
+
+cudaError_t launch_stored_blocks(const Lz77Params& P, cudaStream_t stream)
+{
+    if (P.nseg == 0) return cudaSuccess;
+    stored_blocks_kernel<<<(P.nseg + 255) / 256, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 }  // namespace zsb

@@ -81,10 +81,10 @@ def deflate_sharded(engine, combine, local_in: torch.Tensor, seg_size: int, leve
     if world == 1:
         res.sizes, res.offsets = [out_len], [0]
         res.adler = combine(1, adler, n)
-        res.total_len = out_len + 6
+        res.total_len = out_len + len(final_block(level)) + 4
         if gather_to is not None:
             gather_to[:out_len].copy_(local_out[:out_len])
-            _write_trailer(gather_to, out_len, res.adler)
+            _write_trailer(gather_to, out_len, res.adler, level)
             res.stream = gather_to[:res.total_len]
         return res
     # 2. all_gather of per-rank (compressed bytes, input bytes, adler)
@@ -100,13 +100,13 @@ def deflate_sharded(engine, combine, local_in: torch.Tensor, seg_size: int, leve
     # 3. exclusive scan -> offsets
     res.offsets = exclusive_scan(res.sizes)
     res.adler = combine_adlers(adlers, lengths, combine)
-    res.total_len = sum(res.sizes) + 6
+    res.total_len = sum(res.sizes) + len(final_block(level)) + 4
     # 4. variable-size gather to rank 0
     if gather_on:
         _gather_to_rank0(rank, world, local_out, out_len, res.sizes, res.offsets, gather_to, group)
     # 5. trailer on rank 0
     if rank == 0 and gather_to is not None:
-        _write_trailer(gather_to, sum(res.sizes), res.adler)
+        _write_trailer(gather_to, sum(res.sizes), res.adler, level)
         res.stream = gather_to[:res.total_len]
     return res
 
@@ -209,7 +209,13 @@ def inflate_sharded(engine, combine, local_comp: torch.Tensor, local_ends: torch
     return res
 
 
-def _write_trailer(buf: torch.Tensor, at: int, adler: int):
-    t = torch.tensor([0x03, 0x00, (adler >> 24) & 0xFF, (adler >> 16) & 0xFF, (adler >> 8) & 0xFF, adler & 0xFF],
-                     dtype=torch.uint8, device=buf.device)
-    buf[at:at + 6].copy_(t)
+def final_block(level: int) -> bytes:
+    """What Finish appends after the last full flush: the empty static block `03 00`; at level 0 the empty STORED
+    block `01 00 00 FF FF` (Deflate.Stored.cs:80 with eof)."""
+    return b"\x01\x00\x00\xff\xff" if level == 0 else b"\x03\x00"
+
+
+def _write_trailer(buf: torch.Tensor, at: int, adler: int, level: int) -> int:
+    raw = final_block(level) + bytes([(adler >> 24) & 0xFF, (adler >> 16) & 0xFF, (adler >> 8) & 0xFF, adler & 0xFF])
+    buf[at:at + len(raw)].copy_(torch.tensor(list(raw), dtype=torch.uint8, device=buf.device))
+    return len(raw)

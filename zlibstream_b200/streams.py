@@ -177,7 +177,8 @@ class ZlibOutputStream(io.RawIOBase):
             hdr = (0x78 << 8) | (flevel << 6)
             hdr += 31 - hdr % 31
             tail += bytes([hdr >> 8, hdr & 0xFF])
-        tail += b"\x03\x00" + self._adler.to_bytes(4, "big")
+        from .dist import final_block
+        tail += final_block(int(self.Options.CompressionLevel)) + self._adler.to_bytes(4, "big")
         self.BaseStream.write(tail)
         self._total_out += len(tail)
         self._finished = True

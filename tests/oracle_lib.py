@@ -63,6 +63,23 @@ class Oracle:
         assert rc == 0, rc
         return out.raw[:n.value], list(ends[:nseg]), ad.value
 
+    def deflate_writes(self, data, write_size, level, strategy=0, hv=0, flush_mode=3):
+        """One Write per write_size bytes with Options.FlushMode = flush_mode (0 none, 1 partial, 2 sync, 3 full), then
+        Dispose.  -> (stream bytes, [TotalOut after each Write])"""
+        d = self.lib.zso_deflater_new(level, strategy, flush_mode, hv)
+        assert d
+        ends = []
+        for off in range(0, len(data), write_size):
+            chunk = data[off:off + write_size]
+            assert self.lib.zso_deflater_write(d, chunk, len(chunk)) == 0
+            ends.append(self.lib.zso_deflater_total_out(d))
+        assert self.lib.zso_deflater_finish(d) == 0
+        n = ctypes.c_size_t(0)
+        p = self.lib.zso_deflater_output(d, ctypes.byref(n))
+        out = ctypes.string_at(p, n.value)
+        self.lib.zso_deflater_free(d)
+        return out, ends
+
     def deflate_segments_parallel(self, data, seg_size, level, strategy=0, hv=0, threads=None):
         """deflate_segments on several host threads (ctypes releases the GIL): the stream is cut into contiguous ranges
         of segments, every range after the first is compressed with its PRECEDING segment in front (so the window, the

@@ -54,6 +54,23 @@ def test_level0_stored_blocks(engine, oracle, n, ss):
         engine.deflate_segments(data, ss, 0, 3)
 
 
+@pytest.mark.parametrize("level,strategy", [(1, 0), (3, 0), (6, 0), (9, 0), (6, 1), (6, 2), (6, 3), (1, 4)])
+@pytest.mark.parametrize("ss", [65536, 262144])
+def test_sync_flush_segments(engine, oracle, corpus, level, strategy, ss):
+    """SURVEY 8(f)-3, FlushMode.SyncFlush on every Write (Deflate.cs:583-595): the marker of a full flush, but the hash table
+    stays, so matches reach back into the previous segment.  The stream is one piece for an inflater."""
+    data = (corpus["alice29.txt"] + corpus["ptt5"] + corpus["alice29.txt"] + corpus["kennedy.xls"])[:5 * 262144 + 777]
+    want, want_ends = oracle.deflate_writes(data, ss, level, strategy, 0, flush_mode=2)
+    full, _, _ = oracle.deflate_segments(data, ss, level, strategy)
+    got, ends, adler = engine.deflate_segments(data, ss, level, strategy, sync_flush=True)
+    assert got == want and ends == want_ends and adler == zlib.adler32(data)
+    if strategy in (0, 1, 4):
+        assert len(want) < len(full)          # the second copy of alice29 really is found across the flush points
+    assert zlib.decompress(got) == data
+    dec, ad = engine.inflate_stream(got, len(data))
+    assert dec == data and ad == adler
+
+
 @pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7, 8, 9, -1])
 def test_every_level_matches_oracle(engine, oracle, corpus, level):
     data = corpus["lcet10.txt"] + corpus["sum"] + corpus["ptt5"][:200000]

@@ -12,6 +12,7 @@ ZSB_NO_TRAILER = 0x8
 ZSB_OFFSETS_DEVICE = 0x10
 ZSB_CONTINUATION = 0x20
 ZSB_SINGLE_STREAM = 0x40
+ZSB_SYNC_FLUSH = 0x80
 
 # every symbol include/zsb200.h declares
 EXPORTS = [

@@ -461,6 +461,12 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     // One Write with FlushMode.NoFlush + Dispose (the reference's benchmark call pattern, DeflateCorpusBenchmark.cs:86-99): the
     // whole input is one segment of the stream's first kind whose last block carries BFINAL; no flush marker, no `03 00`.
     const bool single = (flags & ZSB_SINGLE_STREAM) != 0;
+    // FlushMode.SyncFlush on every Write (Deflate.cs:583-595): the same marker as a full flush, but the hash table is kept, so
+    // a segment may refer to the 32 KiB before it.  Segments are then neither independent work (one CTA parses them in
+    // order; HuffmanOnly and Rle, which never read the hash table, keep their parallel path) nor independently decodable.
+    const bool sync_flush = (flags & ZSB_SYNC_FLUSH) != 0;
+    if (sync_flush && (single || first_segment_index != 0 || level == 0))
+        return fail(ctx, ZSB_STREAM_ERROR, "ZSB_SYNC_FLUSH needs the whole stream in one call, level >= 1");
     if (single) {
         if (n > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream holds at most 64 MiB on the device path");
         if (first_segment_index != 0) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream starts at segment 0");
@@ -540,7 +546,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         probe.fn = strategy == ZSB_RLE ? FN_RLE : cfg.fn;
         probe.stats = ctx->lz_stats;
         const char* l1 = getenv("ZSB_L1_KERNEL");
-        use_lists = lz77_lists_applies(probe) && !(l1 && strcmp(l1, "batch") == 0) && !single;
+        use_lists = lz77_lists_applies(probe) && !(l1 && strcmp(l1, "batch") == 0) && !single && !sync_flush;
     }
     const size_t list_bytes_per_seg = use_lists ? lz77_lists_bytes_per_segment((uint32_t)seg_size) : 0;
     const size_t per_seg = sym_bytes_per_seg + list_bytes_per_seg + max_blocks * (sizeof(BlockRec) + sizeof(BlockCodesDev)) + sizeof(uint32_t) + sizeof(SegLayout);
@@ -563,8 +569,9 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     }
     // Host buffers: a few batches, so that the upload of batch b + 1 and the download of batch b - 1's output run beside the
     // kernels of batch b.  Batches are whole multiples of the SM count (the LZ77 kernels hand out one segment per SM at a time).
+    if (sync_flush && batch < nseg) return fail(ctx, ZSB_MEM_ERROR, "ZSB_SYNC_FLUSH: the stream does not fit one batch of scratch");
     bool piped = false;
-    if ((host_in || host_out) && nseg >= (size_t)ctx->num_sms * 16) {
+    if ((host_in || host_out) && nseg >= (size_t)ctx->num_sms * 16 && !sync_flush) {
         size_t pb = (nseg + 3) / 4;
         pb = (pb + ctx->num_sms - 1) / ctx->num_sms * ctx->num_sms;
         if (pb < batch) batch = pb;
@@ -618,6 +625,7 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         L.crc_tab = ctx->crc_tab;
         L.stats = ctx->lz_stats;
         L.lists = use_lists ? ctx->lists.as<uint4>() : nullptr;
+        L.chained = sync_flush ? 1 : 0;
         CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
         timing_mark(ctx, 0, true);
         if (use_lists) {   // an event between the two level-1 kernels: their times are reported apart

@@ -28,6 +28,7 @@ struct Lz77Params {
     // nullptr = not available (the batch parser of zsb_lz77.cu runs instead).  work_counter then points to three counters.
     uint4* lists = nullptr;
     cudaEvent_t ev_mid = nullptr;   // optional: recorded between the two kernels
+    int chained = 0;                // FlushMode.SyncFlush: segments share the hash table and the window (one CTA, in order)
 };
 constexpr int LZ_LIST_K = 10;          // candidates per record
 bool lz77_lists_applies(const Lz77Params& P);

@@ -1096,7 +1096,11 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
         const bool stream_first = (P.first_seg_index + (uint64_t)seg) == 0;
 
         // ---- per-segment init: head zeroed by the previous full flush (Deflate.cs:596-605) ----
-        {
+        // A SYNC flush (P.chained, Deflate.cs:583-595) resets nothing: this CTA has just parsed the previous segment (grid = 1,
+        // segments in order), its hash table, prev[] and window are what the next Write finds, and the parse stands at
+        // window index 32768 with an empty lookahead exactly as after a full flush.
+        const bool carry_over = P.chained && seg > 0;
+        if (!carry_over) {
             uint4 z = make_uint4(0, 0, 0, 0);
             uint4* h4 = reinterpret_cast<uint4*>(sm.head);
             for (int i = tid; i < HASH_SIZE * 2 / 16; i += LZ_THREADS) h4[i] = z;
@@ -1380,7 +1384,7 @@ cudaError_t launch_lz77(const Lz77Params& P, int num_sms, cudaStream_t stream)
     if (!no_symbolize && !P.stats && symbolize_applies(P)) return launch_symbolize(P, num_sms, stream);
     // ZSB_L1_KERNEL=batch keeps level 1 on the batch parser (A/B measurements, parity cross-checks); read per call
     const char* l1 = getenv("ZSB_L1_KERNEL");
-    if (lz77_lists_applies(P) && !(l1 && strcmp(l1, "batch") == 0)) {
+    if (lz77_lists_applies(P) && !P.chained && !(l1 && strcmp(l1, "batch") == 0)) {
         const uint32_t nfull = (uint32_t)(P.n / P.seg_size < P.nseg ? P.n / P.seg_size : P.nseg);
         if (nfull > 0) {
             Lz77Params F = P;
@@ -1419,7 +1423,7 @@ static cudaError_t launch_lz77_classic(const Lz77Params& P, int num_sms, cudaStr
         if (e != cudaSuccess) return e;
     }
     int grid = (int)(P.nseg < (uint32_t)num_sms ? P.nseg : (uint32_t)num_sms);
-    if (grid < 1) grid = 1;
+    if (grid < 1 || P.chained) grid = 1;   // chained segments (sync flush) are one CTA's, in order
     // ZSB_SLOW_THREADS=256 keeps levels 4-9 on the 256-thread kernel (A/B measurements)
     static const bool slow_wide = [] {
         const char* e = getenv("ZSB_SLOW_THREADS");

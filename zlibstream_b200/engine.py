@@ -91,8 +91,9 @@ class Engine:
     # -- host-buffer API --------------------------------------------------------------------------
     def deflate_segments(self, data, seg_size: int, level: int, strategy: int = 0,
                          hash_variant: int = HashVariant.Crc32C, first_segment_index: int = 0, halo=None,
-                         header: bool = True, trailer: bool = True):
-        """Returns (compressed bytes, list of segment end offsets, adler32 of data)."""
+                         header: bool = True, trailer: bool = True, sync_flush: bool = False):
+        """Returns (compressed bytes, list of segment end offsets, adler32 of data).  sync_flush: every Write ends with
+        FlushMode.SyncFlush instead of FullFlush (segments share the hash table: serial on the device, one-piece to inflate)."""
         addr, n, keep = _addr(data)
         nseg = (n + seg_size - 1) // seg_size if seg_size else 0
         cap = self.deflate_bound(n, seg_size)
@@ -101,6 +102,7 @@ class Engine:
         ends = (ctypes.c_uint64 * max(nseg, 1))()
         adler = ctypes.c_uint32(0)
         flags = (0 if header else _native.ZSB_NO_HEADER) | (0 if trailer else _native.ZSB_NO_TRAILER)
+        flags |= _native.ZSB_SYNC_FLUSH if sync_flush else 0
         haddr, hkeep = 0, None
         if halo is not None:
             haddr, hn, hkeep = _addr(halo)

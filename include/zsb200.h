@@ -162,6 +162,23 @@ ZSB_API int zsb_inflate_fill_carry(zsb_ctx* ctx, uint8_t prev_byte, uint32_t* ad
 ZSB_API int zsb_build_segment_index(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size, unsigned flags,
                                     uint64_t* seg_end_offsets, size_t cap, size_t* nseg, uint64_t* uncompressed_size);
 
+/*
+ * PNG front end: the caller the reference is written for is ImageSharp's PNG encoder
+ * (/root/reference/readme.md:22), which filters scanlines on the CPU and streams them through ZlibOutputStream.  Here the
+ * pixels are filtered on the device (PNG specification section 9; filter 5 = the minimum-sum-of-absolute-differences choice per
+ * scanline of section 12.8), compressed as full-flush segments by zsb_deflate_segments (so the IDAT payload is bit-identical to
+ * what the reference writes for the same filtered bytes), check-summed (CRC-32 of every IDAT chunk) and framed: the result is a
+ * complete PNG file (signature, IHDR, IDAT..., IEND).  8 bits per sample; color_type 0 gray, 2 RGB, 4 gray + alpha, 6 RGBA.
+ *
+ *   seg_size     full-flush segment size of the IDAT stream (0 = 65536)
+ *   idat_bytes   zlib bytes per IDAT chunk, a multiple of 65536 (0 = one chunk if the stream fits, else 1 GiB chunks)
+ *   flags        ZSB_IN_DEVICE / ZSB_OUT_DEVICE
+ */
+ZSB_API size_t zsb_png_bound(uint32_t width, uint32_t height, int color_type, size_t seg_size, size_t idat_bytes);
+ZSB_API int zsb_png_encode(zsb_ctx* ctx, const void* pixels, uint32_t width, uint32_t height, int color_type, int filter,
+                           int level, int strategy, size_t seg_size, size_t idat_bytes, unsigned flags, void* out,
+                           size_t out_cap, size_t* out_len);
+
 /* Replaces Adler32.Calculate(adler, span) (Adler32.cs:51-78). flags: ZSB_IN_DEVICE. */
 ZSB_API int zsb_adler32(zsb_ctx* ctx, uint32_t seed, const void* p, size_t n, unsigned flags, uint32_t* result);
 /* adler32_combine; absent from the reference. Pure host function. */

@@ -127,3 +127,25 @@ def test_parallel_oracle_equals_the_single_thread_call(oracle, corpus, level, st
     want = oracle.deflate_segments(data, ss, level, strategy)
     got = oracle.deflate_segments_parallel(data, ss, level, strategy, threads=5)
     assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
+
+
+def test_png_reference_round_trip():
+    """oracle/png_ref.py (the checker of the device PNG front end): filter -> frame with stock zlib -> decode == pixels."""
+    import struct
+    import sys
+    import zlib
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import png_ref
+    for ct in (0, 2, 4, 6):
+        w, h, ch = 37, 19, png_ref.CHANNELS[ct]
+        px = np.random.RandomState(ct).randint(0, 256, size=(h, w, ch)).astype(np.uint8).tobytes()
+        for f in range(6):
+            filt = png_ref.filter_image(px, w, h, ct, f)
+
+            def chunk(t, d):
+                return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+            png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ct, 0, 0, 0)) + \
+                chunk(b"IDAT", zlib.compress(filt)) + chunk(b"IEND", b"")
+            assert png_ref.decode(png)["pixels"] == px

@@ -18,7 +18,7 @@ ZSB_SYNC_FLUSH = 0x80
 EXPORTS = [
     "zsb_ctx_create", "zsb_ctx_destroy", "zsb_last_error", "zsb_ctx_set_stream", "zsb_ctx_get_stream",
     "zsb_ctx_launch_count", "zsb_ctx_last_kernel_ms", "zsb_ctx_last_kernel_ms_detail", "zsb_deflate_bound", "zsb_deflate_segments",
-    "zsb_inflate_segments", "zsb_ctx_last_inflate_carry", "zsb_inflate_fill_carry", "zsb_build_segment_index", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
+    "zsb_inflate_segments", "zsb_ctx_last_inflate_carry", "zsb_inflate_fill_carry", "zsb_build_segment_index", "zsb_png_bound", "zsb_png_encode", "zsb_adler32", "zsb_adler32_combine", "zsb_version", "zsb_debug_fetch",
 ]
 
 _lib = None
@@ -69,6 +69,10 @@ def load():
     lib.zsb_inflate_fill_carry.restype = i32
     lib.zsb_build_segment_index.argtypes = [vp, vp, sz, sz, c.c_uint, vp, sz, c.POINTER(sz), c.POINTER(u64)]
     lib.zsb_build_segment_index.restype = i32
+    lib.zsb_png_bound.argtypes = [u32, u32, i32, sz, sz]
+    lib.zsb_png_bound.restype = sz
+    lib.zsb_png_encode.argtypes = [vp, vp, u32, u32, i32, i32, i32, i32, sz, sz, c.c_uint, vp, sz, c.POINTER(sz)]
+    lib.zsb_png_encode.restype = i32
     lib.zsb_adler32.argtypes = [vp, u32, vp, sz, c.c_uint, c.POINTER(u32)]
     lib.zsb_adler32.restype = i32
     lib.zsb_adler32_combine.argtypes = [u32, u32, u64]

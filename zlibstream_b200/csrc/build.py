@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["zsb_api.cu", "zsb_lz77.cu", "zsb_lz77_lists.cu", "zsb_lz77_resolve.cu", "zsb_symbolize.cu", "zsb_huffman.cu", "zsb_inflate.cu", "zsb_inflate_lanes.cu", "zsb_inflate_lanes_small.cu", "zsb_adler32.cu"]
+SOURCES = ["zsb_api.cu", "zsb_lz77.cu", "zsb_lz77_lists.cu", "zsb_lz77_resolve.cu", "zsb_symbolize.cu", "zsb_huffman.cu", "zsb_inflate.cu", "zsb_inflate_lanes.cu", "zsb_inflate_lanes_small.cu", "zsb_adler32.cu", "zsb_png.cu"]
 HEADERS = ["zsb_common.cuh", "zsb_kernels.cuh", "zsb_lz77_dev.cuh", "zsb_inflate_lanes.cuh", "zsb_inflate_lanes.cu", os.path.join("..", "..", "include", "zsb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -82,7 +82,7 @@ struct zsb_ctx {
     size_t last_inflate_produced = 0;
     bool last_inflate_valid = false;
     // scratch
-    DevBuf lists, in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry, idx_cand;
+    DevBuf lists, in_stage, out_stage, sym, blocks, nblocks, codes, layout, seg_adler, seg_end, small, halo_stage, inf_len, inf_status, inf_scratch, inf_carry, idx_cand, png_raw, png_filt, png_z, png_crc, png_out;
     uint16_t* crc_tab = nullptr;
     unsigned long long* lz_stats = nullptr;  // 32 counters, only with ZSB_LZ_STATS=1
     // timing of the last call
@@ -359,7 +359,7 @@ void zsb_ctx_destroy(zsb_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     DevBuf* bufs[] = {&ctx->lists, &ctx->in_stage, &ctx->out_stage, &ctx->sym, &ctx->blocks, &ctx->nblocks, &ctx->codes, &ctx->layout,
-                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status, &ctx->inf_scratch, &ctx->inf_carry, &ctx->idx_cand};
+                      &ctx->seg_adler, &ctx->seg_end, &ctx->small, &ctx->halo_stage, &ctx->inf_len, &ctx->inf_status, &ctx->inf_scratch, &ctx->inf_carry, &ctx->idx_cand, &ctx->png_raw, &ctx->png_filt, &ctx->png_z, &ctx->png_crc, &ctx->png_out};
     for (DevBuf* b : bufs) b->release();
     if (ctx->crc_tab) cudaFree(ctx->crc_tab);
     if (ctx->lz_stats) cudaFree(ctx->lz_stats);
@@ -434,6 +434,137 @@ int zsb_ctx_last_kernel_ms_detail(const zsb_ctx* cctx, float* out, int n)
     cudaStreamSynchronize(ctx->stream);
     timing_collect(ctx);
     for (int i = 0; i < n; i++) out[i] = i < 5 ? ctx->ms[i] : 0.f;
+    return ZSB_OK;
+}
+
+// ---- PNG front end ---------------------------------------------------------------------------------------------
+namespace {
+int png_channels(int color_type) { return color_type == 0 ? 1 : color_type == 2 ? 3 : color_type == 4 ? 2 : color_type == 6 ? 4 : 0; }
+void put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+__global__ void png_put_crcs_kernel(uint8_t* out, const uint32_t* crc, uint32_t nidat, size_t first_pos, size_t idat_bytes, size_t zlen)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nidat) return;
+    // IDAT k: [len 4]["IDAT" 4][data][crc 4]; data of IDAT j < k is idat_bytes long
+    const size_t data_end = ((size_t)(k + 1) * idat_bytes < zlen) ? (size_t)(k + 1) * idat_bytes : zlen;
+    const size_t pos = first_pos + (size_t)k * 12 + 8 + data_end;
+    const uint32_t v = crc[k];
+    out[pos] = (uint8_t)(v >> 24);
+    out[pos + 1] = (uint8_t)(v >> 16);
+    out[pos + 2] = (uint8_t)(v >> 8);
+    out[pos + 3] = (uint8_t)v;
+}
+size_t png_default_idat(size_t zbound) { return zbound <= 0x7FFF0000ull ? 0x7FFF0000ull : (size_t)1 << 30; }
+}  // namespace
+
+size_t zsb_png_bound(uint32_t width, uint32_t height, int color_type, size_t seg_size, size_t idat_bytes)
+{
+    const int ch = png_channels(color_type);
+    if (!ch) return 0;
+    if (!seg_size) seg_size = 65536;
+    const size_t filt = (size_t)height * ((size_t)width * ch + 1);
+    const size_t z = zsb_deflate_bound(filt, seg_size);
+    if (!idat_bytes) idat_bytes = png_default_idat(z);
+    return 8 + 25 + z + ((z + idat_bytes - 1) / idat_bytes + 1) * 12 + 12;
+}
+
+int zsb_png_encode(zsb_ctx* ctx, const void* pixels, uint32_t width, uint32_t height, int color_type, int filter, int level,
+                   int strategy, size_t seg_size, size_t idat_bytes, unsigned flags, void* out, size_t out_cap, size_t* out_len)
+{
+    if (!ctx) return ZSB_STREAM_ERROR;
+    ctx->err.clear();
+    if (out_len) *out_len = 0;
+    const int ch = png_channels(color_type);
+    if (!ch) return fail(ctx, ZSB_STREAM_ERROR, "color_type must be 0 (gray), 2 (RGB), 4 (gray + alpha) or 6 (RGBA), 8 bits per sample");
+    if (!pixels || !out || width == 0 || height == 0) return fail(ctx, ZSB_STREAM_ERROR, "stream error");
+    if (filter < 0 || filter > 5) return fail(ctx, ZSB_STREAM_ERROR, "filter must be 0..4 (PNG filter types) or 5 (adaptive)");
+    if (!seg_size) seg_size = 65536;
+    const size_t rowbytes = (size_t)width * ch;
+    if (rowbytes > 0x7FFFFFF0ull) return fail(ctx, ZSB_STREAM_ERROR, "scanline too long");
+    const size_t raw_bytes = rowbytes * height, filt_bytes = (rowbytes + 1) * height;
+    const size_t zcap = zsb_deflate_bound(filt_bytes, seg_size);
+    if (!idat_bytes) idat_bytes = png_default_idat(zcap);
+    if (idat_bytes % kCrcChunk || idat_bytes > 0x7FFF0000ull) return fail(ctx, ZSB_STREAM_ERROR, "idat_bytes must be a multiple of 65536 below 2 GiB");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    const uint8_t* d_px = reinterpret_cast<const uint8_t*>(pixels);
+    if (!(flags & ZSB_IN_DEVICE)) {
+        CU(ctx->png_raw.reserve(raw_bytes));
+        CU(cudaMemcpyAsync(ctx->png_raw.p, pixels, raw_bytes, cudaMemcpyHostToDevice, st));
+        d_px = ctx->png_raw.as<uint8_t>();
+    }
+    CU(ctx->png_filt.reserve(filt_bytes));
+    CU(ctx->png_z.reserve(zcap + 16));
+    PngFilterParams F;
+    F.px = d_px;
+    F.out = ctx->png_filt.as<uint8_t>();
+    F.rowbytes = (uint32_t)rowbytes;
+    F.height = height;
+    F.bpp = (uint32_t)ch;
+    F.filter = filter;
+    CU(launch_png_filter(F, st));
+    ctx->launches++;
+
+    // the filtered scanlines are the deflater's input: full-flush segments, exactly what the reference would emit for them
+    size_t zlen = 0;
+    uint32_t adler = 0;
+    int rc = zsb_deflate_segments(ctx, ctx->png_filt.p, filt_bytes, seg_size, level, strategy, ZSB_HASH_CRC32C, 0, nullptr,
+                                  ZSB_IN_DEVICE | ZSB_OUT_DEVICE, ctx->png_z.p, zcap, &zlen, nullptr, &adler);
+    if (rc != ZSB_OK) return rc;
+
+    const size_t nchunks = (zlen + kCrcChunk - 1) / kCrcChunk;
+    const uint32_t nidat = (uint32_t)((zlen + idat_bytes - 1) / idat_bytes);
+    CU(ctx->png_crc.reserve((nchunks + nidat + 2) * sizeof(uint32_t)));
+    uint32_t* d_chunk_crc = ctx->png_crc.as<uint32_t>();
+    uint32_t* d_idat_crc = d_chunk_crc + nchunks;
+    CU(launch_crc32_chunks(ctx->png_z.as<uint8_t>(), zlen, d_chunk_crc, st));
+    CU(launch_png_idat_crc(d_chunk_crc, zlen, idat_bytes, nidat, d_idat_crc, st));
+    ctx->launches += 2;
+
+    const size_t total = 8 + 25 + zlen + (size_t)nidat * 12 + 12;
+    if (out_len) *out_len = total;
+    if (total > out_cap) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+    uint8_t* d_dst = reinterpret_cast<uint8_t*>(out);
+    if (!(flags & ZSB_OUT_DEVICE)) {
+        CU(ctx->png_out.reserve(total));
+        d_dst = ctx->png_out.as<uint8_t>();
+    }
+    // signature, IHDR
+    uint8_t head[33] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A, 0, 0, 0, 13, 'I', 'H', 'D', 'R'};
+    put_be32(head + 16, width);
+    put_be32(head + 20, height);
+    head[24] = 8;                    // bit depth
+    head[25] = (uint8_t)color_type;
+    head[26] = 0;                    // compression method: deflate
+    head[27] = 0;                    // filter method 0
+    head[28] = 0;                    // no interlace
+    put_be32(head + 29, crc32_host(head + 12, 17));
+    CU(cudaMemcpyAsync(d_dst, head, sizeof head, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // `head` is a stack buffer
+    std::vector<uint8_t> hdrs((size_t)nidat * 8);
+    size_t pos = 33;
+    for (uint32_t k = 0; k < nidat; k++) {
+        const size_t b = (size_t)k * idat_bytes, e = std::min(zlen, b + idat_bytes);
+        uint8_t* h = hdrs.data() + (size_t)k * 8;
+        put_be32(h, (uint32_t)(e - b));
+        h[4] = 'I'; h[5] = 'D'; h[6] = 'A'; h[7] = 'T';
+        CU(cudaMemcpyAsync(d_dst + pos, h, 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_dst + pos + 8, ctx->png_z.as<uint8_t>() + b, e - b, cudaMemcpyDeviceToDevice, st));
+        pos += 8 + (e - b) + 4;
+    }
+    if (nidat) {
+        png_put_crcs_kernel<<<(nidat + 63) / 64, 64, 0, st>>>(d_dst, d_idat_crc, nidat, 33, idat_bytes, zlen);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    static const uint8_t kIend[12] = {0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xAE, 0x42, 0x60, 0x82};
+    CU(cudaMemcpyAsync(d_dst + pos, kIend, 12, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    if (!(flags & ZSB_OUT_DEVICE)) {
+        CU(cudaMemcpyAsync(out, d_dst, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     return ZSB_OK;
 }
 

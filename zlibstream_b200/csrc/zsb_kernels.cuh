@@ -135,6 +135,23 @@ cudaError_t launch_inflate_carry_fixup(const InflateParams& P, cudaStream_t stre
 cudaError_t launch_index_markers(const uint8_t* in, size_t begin, size_t end, uint64_t* cand, uint32_t cand_cap, uint32_t* ncand,
                                  cudaStream_t stream);
 
+// ---- PNG front end (zsb_png.cu) ---------------------------------------------------------------------------------------
+struct PngFilterParams {
+    const uint8_t* px;     // [height][rowbytes] raw samples, 8 bits each
+    uint8_t* out;          // [height][1 + rowbytes]: filter type byte + filtered bytes
+    uint32_t rowbytes, height, bpp;
+    int filter;            // 0 None, 1 Sub, 2 Up, 3 Average, 4 Paeth, 5 adaptive (per row)
+};
+cudaError_t launch_png_filter(const PngFilterParams& P, cudaStream_t stream);
+constexpr uint32_t kCrcChunk = 1u << 16;
+struct CrcMults { uint32_t level[8], chunk, x8; };
+uint32_t crc32_host(const uint8_t* p, size_t n);
+uint32_t crc32_combine_host(uint32_t crc1, uint32_t crc2, uint64_t len2);
+// CRC-32 of every kCrcChunk bytes of p (the last chunk may be shorter)
+cudaError_t launch_crc32_chunks(const uint8_t* p, size_t n, uint32_t* chunk_crc, cudaStream_t stream);
+// crc("IDAT" || bytes of IDAT k) for IDAT chunks of idat_bytes (a multiple of kCrcChunk) stream bytes each
+cudaError_t launch_png_idat_crc(const uint32_t* chunk_crc, size_t n, size_t idat_bytes, uint32_t nidat, uint32_t* out, cudaStream_t stream);
+
 enum InflateErr {
     IE_OK = 0, IE_BLOCK_TYPE, IE_STORED_LEN, IE_TOO_MANY_SYMS, IE_BAD_REPEAT, IE_OVERSUB_BL, IE_INCOMPLETE_BL,
     IE_OVERSUB_L, IE_INCOMPLETE_L, IE_OVERSUB_D, IE_INCOMPLETE_D, IE_EMPTY_D, IE_BAD_LCODE, IE_BAD_DCODE,

@@ -176,6 +176,32 @@ class Engine:
         del keep
         return list(ends)[:nseg.value], total.value
 
+    def png_encode(self, pixels, width: int, height: int, color_type: int = 6, filter: int = 5, level: int = 6,
+                   strategy: int = 1, seg_size: int = 65536, idat_bytes: int = 0) -> bytes:
+        """A complete PNG file from 8-bit samples (host buffer, row-major, no padding): filtered, deflated, check-summed and
+        framed on the device (zsb_png_encode).  filter 0..4 = PNG filter types, 5 = adaptive per scanline."""
+        addr, n, keep = _addr(pixels)
+        cap = int(self._lib.zsb_png_bound(width, height, color_type, seg_size, idat_bytes))
+        if cap == 0:
+            raise ValueError("color_type")
+        out = ctypes.create_string_buffer(cap)
+        out_len = ctypes.c_size_t(0)
+        rc = self._lib.zsb_png_encode(self._h, addr, width, height, color_type, filter, int(level), int(strategy), seg_size,
+                                      idat_bytes, 0, out, cap, ctypes.byref(out_len))
+        self._check(rc, True)
+        del keep
+        return out.raw[:out_len.value]
+
+    def png_encode_device(self, px_ptr: int, width: int, height: int, color_type: int, filter: int, level: int, strategy: int,
+                          out_ptr: int, out_cap: int, seg_size: int = 65536, idat_bytes: int = 0) -> int:
+        """Device pointers in and out; returns the PNG's length."""
+        out_len = ctypes.c_size_t(0)
+        rc = self._lib.zsb_png_encode(self._h, px_ptr, width, height, color_type, filter, int(level), int(strategy), seg_size,
+                                      idat_bytes, _native.ZSB_IN_DEVICE | _native.ZSB_OUT_DEVICE, out_ptr, out_cap,
+                                      ctypes.byref(out_len))
+        self._check(rc, True)
+        return out_len.value
+
     def adler32(self, data, seed: int = 1) -> int:
         addr, n, keep = _addr(data)
         res = ctypes.c_uint32(0)

@@ -185,12 +185,41 @@ def test_stream_classes_round_trip(engine, oracle, corpus):
     assert bytes(got) == data and zi.Adler == zlib.adler32(data)
 
 
+def test_stream_classes_other_flush_modes(engine, oracle, corpus):
+    """FlushMode.NoFlush (the options' default, ZlibOptions.cs:14-24) = one Write + Dispose: the reference's published size;
+    FlushMode.SyncFlush: the oracle's stream for the same Writes; both read back as one piece.  Bounded read-ahead without a
+    side-car for a full-flush stream."""
+    from zlibstream_b200 import CompressionLevel, FlushMode, ZlibInputStream, ZlibOptions, ZlibOutputStream
+    data = corpus["alice29.txt"]
+    sink = io.BytesIO()
+    z = ZlibOutputStream(sink, ZlibOptions(CompressionLevel=CompressionLevel.Level6), engine=engine)
+    z.Write(data, 0, len(data))
+    z.close()
+    assert len(sink.getvalue()) == 55818 and sink.getvalue() == oracle.deflate_oneshot(data, 6)[0]
+    zi = ZlibInputStream(io.BytesIO(sink.getvalue()), segment_size=None, uncompressed_size=len(data), engine=engine)
+    assert zi.read() == data and zi.Adler == zlib.adler32(data)
+    big = b"".join(corpus[k] for k in sorted(corpus))
+    sink = io.BytesIO()
+    z = ZlibOutputStream(sink, ZlibOptions(CompressionLevel=CompressionLevel.Level6, FlushMode=FlushMode.SyncFlush), engine=engine)
+    for off in range(0, len(big), 65536):
+        z.Write(big, off, min(65536, len(big) - off))
+    z.close()
+    want, want_ends = oracle.deflate_writes(big, 65536, 6, 0, 0, flush_mode=2)
+    assert sink.getvalue() == want and z.SegmentEndOffsets == want_ends
+    zi = ZlibInputStream(io.BytesIO(want), segment_size=None, uncompressed_size=len(big), engine=engine)
+    assert zi.read() == big
+    full, ends, adler = oracle.deflate_segments(big, 65536, 1)
+    zi = ZlibInputStream(io.BytesIO(full), segment_size=65536, engine=engine, batch_segments=8)   # several read-ahead batches
+    assert zi.read() == big and zi.Adler == adler and zi.TotalIn == len(full)
+
+
 def test_stream_class_argument_behaviour(engine):
     from zlibstream_b200 import CompressionLevel, FlushMode, ZlibOptions, ZlibOutputStream, ZlibStreamException
     with pytest.raises(ValueError):
         ZlibOutputStream(None, CompressionLevel.Level6, engine=engine)
-    z = ZlibOutputStream(io.BytesIO(), ZlibOptions(CompressionLevel=CompressionLevel.Level6), engine=engine)
-    with pytest.raises(ZlibStreamException, match="deflating: "):   # NoFlush is not on the device path
+    z = ZlibOutputStream(io.BytesIO(), ZlibOptions(CompressionLevel=CompressionLevel.Level6, FlushMode=FlushMode.PartialFlush),
+                         engine=engine)
+    with pytest.raises(ZlibStreamException, match="deflating: "):   # PartialFlush is not on the device path
         z.write(b"x" * 65536)
     with pytest.raises(io.UnsupportedOperation):
         z.seek(0)

@@ -105,10 +105,20 @@ int cuda_fail(zsb_ctx* c, cudaError_t e, const char* what)
 {
     return fail(c, e == cudaErrorMemoryAllocation ? ZSB_MEM_ERROR : ZSB_ERRNO, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CU(call)                                                  \
-    do {                                                          \
-        cudaError_t e__ = (call);                                 \
-        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+// An error return must not leave copies in flight against the caller's host buffers (the piped deflate path queues them on
+// copy_stream): both streams are drained before the error goes back.
+int cuda_fail_sync(zsb_ctx* c, cudaError_t e, const char* what)
+{
+    if (c) {
+        cudaStreamSynchronize(c->stream);
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    }
+    return cuda_fail(c, e, what);
+}
+#define CU(call)                                                       \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return cuda_fail_sync(ctx, e__, #call); \
     } while (0)
 
 void crc32c_slices(uint16_t* out /* 4*256 */)
@@ -226,17 +236,24 @@ int build_segment_index(zsb_ctx* ctx, const uint8_t* d_in, size_t n, uint64_t fi
     if (total_bytes) *total_bytes = 0;
     if (body_end <= first) return ZSB_OK;
     cudaStream_t st = ctx->stream;
-    const size_t cap = std::max<size_t>(1u << 20, (body_end - first) / 64 + 1024);
+    size_t cap = std::max<size_t>(1u << 20, (body_end - first) / 64 + 1024);
     CU(ctx->idx_cand.reserve(cap * sizeof(uint64_t)));
     uint8_t* small = ctx->small.as<uint8_t>();
     uint32_t* d_ncand = reinterpret_cast<uint32_t*>(small + 24);
     unsigned int* d_work = reinterpret_cast<unsigned int*>(small + 16);
-    CU(cudaMemsetAsync(d_ncand, 0, sizeof(uint32_t), st));
-    CU(launch_index_markers(d_in, first, body_end, ctx->idx_cand.as<uint64_t>(), (uint32_t)std::min<size_t>(cap, 0xFFFFFFFFu), d_ncand, st));
-    ctx->launches++;
     uint32_t ncand = 0;
-    CU(cudaMemcpyAsync(&ncand, d_ncand, sizeof ncand, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU(cudaMemsetAsync(d_ncand, 0, sizeof(uint32_t), st));
+        CU(launch_index_markers(d_in, first, body_end, ctx->idx_cand.as<uint64_t>(), (uint32_t)std::min<size_t>(cap, 0xFFFFFFFFu), d_ncand, st));
+        ctx->launches++;
+        CU(cudaMemcpyAsync(&ncand, d_ncand, sizeof ncand, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ncand <= cap) break;
+        // more occurrences of 00 00 FF FF than the first guess holds (level-0 streams, data that contains the pattern): the
+        // kernel has counted them all, so grow the list to that count and scan again
+        cap = ncand;
+        CU(ctx->idx_cand.reserve(cap * sizeof(uint64_t)));
+    }
     if (ncand > cap) return fail(ctx, ZSB_DATA_ERROR, "too many full-flush marker candidates");
     std::vector<uint64_t> cand(ncand);
     if (ncand) CU(cudaMemcpyAsync(cand.data(), ctx->idx_cand.p, ncand * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -853,6 +870,20 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     return ZSB_OK;
 }
 
+// The final block Finish appends after the last full flush: the empty static block `03 00` (Q12) or, for a level-0 stream, the
+// empty STORED block `01 00 00 FF FF` (Deflate.Stored.cs:80 with eof) -- 6 or 9 bytes with the Adler-32.
+static int segmented_trailer_len(zsb_ctx* ctx, const void* in, size_t n, unsigned flags, size_t* len)
+{
+    *len = 6;
+    if (n < 9) return ZSB_OK;
+    uint8_t tail9[9];
+    if (flags & ZSB_IN_DEVICE) CU(cudaMemcpy(tail9, reinterpret_cast<const uint8_t*>(in) + n - 9, 9, cudaMemcpyDeviceToHost));
+    else memcpy(tail9, reinterpret_cast<const uint8_t*>(in) + n - 9, 9);
+    static const uint8_t kStoredFinal[5] = {0x01, 0x00, 0x00, 0xFF, 0xFF};
+    if (!(tail9[3] == 0x03 && tail9[4] == 0x00) && memcmp(tail9, kStoredFinal, 5) == 0) *len = 9;
+    return ZSB_OK;
+}
+
 int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t* seg_end_offsets, size_t nseg,
                          size_t seg_size, unsigned flags, void* out, size_t out_cap, size_t* out_len, uint32_t* adler)
 {
@@ -865,14 +896,10 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     // a one-piece stream (written without full flushes) is one segment that ends with its final block; its trailer is the
     // Adler-32 alone (Inflate.cs:286-342)
     size_t trailer_len = has_trailer ? (single ? 4u : 6u) : 0u;
-    if (has_trailer && !single && n >= 9) {
-        // the final block Finish appends: the empty static block `03 00` (Q12) or, for a level-0 stream, the empty STORED block
-        // `01 00 00 FF FF` (Deflate.Stored.cs:80 with eof) -- 6 or 9 bytes with the Adler-32
-        uint8_t tail9[9];
-        if (flags & ZSB_IN_DEVICE) CU(cudaMemcpy(tail9, reinterpret_cast<const uint8_t*>(in) + n - 9, 9, cudaMemcpyDeviceToHost));
-        else memcpy(tail9, reinterpret_cast<const uint8_t*>(in) + n - 9, 9);
-        static const uint8_t kStoredFinal[5] = {0x01, 0x00, 0x00, 0xFF, 0xFF};
-        if (!(tail9[3] == 0x03 && tail9[4] == 0x00) && memcmp(tail9, kStoredFinal, 5) == 0) trailer_len = 9;
+    if (has_trailer && !single) {
+        CU(cudaSetDevice(ctx->device));
+        int rc = segmented_trailer_len(ctx, in, n, flags, &trailer_len);
+        if (rc != ZSB_OK) return rc;
     }
     uint64_t single_end = 0;
     if (single) {
@@ -1058,7 +1085,12 @@ int zsb_build_segment_index(zsb_ctx* ctx, const void* in, size_t n, size_t seg_s
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const bool has_header = !(flags & ZSB_NO_HEADER), has_trailer = !(flags & ZSB_NO_TRAILER);
-    if (n < (has_header ? 2u : 0u) + (has_trailer ? 6u : 0u)) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+    size_t trailer_len = 0;
+    if (has_trailer) {
+        int rc = segmented_trailer_len(ctx, in, n, flags, &trailer_len);
+        if (rc != ZSB_OK) return rc;
+    }
+    if (n < (has_header ? 2u : 0u) + trailer_len) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
     const uint8_t* d_in = reinterpret_cast<const uint8_t*>(in);
     if (!(flags & ZSB_IN_DEVICE)) {
         CU(ctx->in_stage.reserve(n ? n : 1));
@@ -1067,7 +1099,7 @@ int zsb_build_segment_index(zsb_ctx* ctx, const void* in, size_t n, size_t seg_s
     }
     std::vector<uint64_t> ends;
     uint64_t total = 0;
-    int rc = build_segment_index(ctx, d_in, n, has_header ? 2 : 0, n - (has_trailer ? 6 : 0), seg_size, ends, &total);
+    int rc = build_segment_index(ctx, d_in, n, has_header ? 2 : 0, n - trailer_len, seg_size, ends, &total);
     if (rc != ZSB_OK) return rc;
     *nseg = ends.size();
     if (uncompressed_size) *uncompressed_size = total;

@@ -167,11 +167,15 @@ class Engine:
         flags = (0 if header else _native.ZSB_NO_HEADER) | (0 if trailer else _native.ZSB_NO_TRAILER)
         nseg = ctypes.c_size_t(0)
         total = ctypes.c_uint64(0)
-        rc = self._lib.zsb_build_segment_index(self._h, addr, n, seg_size, flags, None, 0, ctypes.byref(nseg), ctypes.byref(total))
-        self._check(rc, False)
-        ends = (ctypes.c_uint64 * max(nseg.value, 1))()
-        rc = self._lib.zsb_build_segment_index(self._h, addr, n, seg_size, flags, ends, nseg.value, ctypes.byref(nseg),
-                                               ctypes.byref(total))
+        # one call scans, validates and fills; 64 KiB of anything compresses to more than 64 bytes, so n / 64 slots nearly always
+        # suffice (the library reports the count with ZBUFERROR if they do not, and the call is repeated once)
+        cap = n // 64 + 16
+        ends = (ctypes.c_uint64 * cap)()
+        rc = self._lib.zsb_build_segment_index(self._h, addr, n, seg_size, flags, ends, cap, ctypes.byref(nseg), ctypes.byref(total))
+        if rc == CompressionState.ZBUFERROR and nseg.value > cap:
+            cap = nseg.value
+            ends = (ctypes.c_uint64 * cap)()
+            rc = self._lib.zsb_build_segment_index(self._h, addr, n, seg_size, flags, ends, cap, ctypes.byref(nseg), ctypes.byref(total))
         self._check(rc, False)
         del keep
         return list(ends)[:nseg.value], total.value

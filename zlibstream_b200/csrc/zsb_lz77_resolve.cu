@@ -243,6 +243,11 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 4) lz77_resolve_kernel(Lz77Para
                         r_dist = seld;
                         r_cnt = __popc(V4);
                         r_over = more && !nice_hit && r_cnt < chain;
+                        // the walk will need the record of the last listed node if the parse lands here: ask for it now
+                        if (r_over && nk > 0) {
+                            const uint4* nr = rec + (size_t)(a - (int)dist_at(r0, r1.x, nk - 1)) * 2;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nr));
+                        }
                     }
                     uint32_t OVm = __ballot_sync(0xffffffffu, r_over);
                     uint32_t Mm = __ballot_sync(0xffffffffu, r_len >= MIN_MATCH);
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 4) lz77_resolve_kernel(Lz77Para
                             int cnt = 0, best = MIN_MATCH - 1, seld = 0;
                             bool done = false;
                             const int nice = la < nice_cfg ? la : nice_cfg;
-#pragma unroll
+#pragma unroll 1   // the rare path: a rolled loop keeps its ten candidates out of the registers of the short path
                             for (int j = 0; j < LZ_LIST_K; j++) {
                                 if (!done && j < nk) {
                                     const int d = (int)dist[j];

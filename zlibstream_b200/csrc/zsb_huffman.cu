@@ -27,8 +27,12 @@ __constant__ uint8_t c_extra_blbits[BL_CODES] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
 __constant__ uint8_t c_bl_order[BL_CODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 struct TreeWork {            // scratch of one Build_tree run (Deflate.Buffers.cs:17-85)
-    uint16_t heap[HEAP_SIZE + 3];
-    uint8_t depth[HEAP_SIZE + 3];
+    uint16_t heap[HEAP_SIZE + 3];   // the nodes in the order they leave the heap (Gen_bitlen walks it), filled from the top
+    // The live heap, one word per entry: frequency << 18 | depth << 10 | node.  Smaller (Trees.cs:556: lower frequency, or the
+    // same frequency and depth not greater) is then `(a >> 10) <= (b >> 10)` on words that are already loaded -- one shared-
+    // memory round trip per heap level instead of three dependent ones (index -> frequency -> depth).  Frequencies that are
+    // compared stay below 2^14 (a block holds 16383 symbols + END_BLOCK; only the root reaches 16384 and it is never compared).
+    uint32_t hk[HEAP_SIZE + 3];
     uint16_t bl_count[MAX_BITS + 1];
     int heap_len, heap_max;
     int opt_len, static_len;
@@ -44,23 +48,24 @@ __device__ __forceinline__ int tree_extra(int kind, int n)
 }
 __device__ __forceinline__ int tree_static_len(int kind, int n) { return kind == TK_L ? static_llen(n) : 5; }
 
-__device__ __forceinline__ bool node_smaller(const CodeData* tree, int n, int m, const uint8_t* depth)  // Trees.cs:556
-{
-    return tree[n].fc < tree[m].fc || (tree[n].fc == tree[m].fc && depth[n] <= depth[m]);
-}
+__device__ __forceinline__ uint32_t heap_entry(uint32_t freq, uint32_t depth, int node) { return (freq << 18) | (depth << 10) | (uint32_t)node; }
 
-__device__ void pq_down_heap(TreeWork& w, const CodeData* tree, int k)  // Trees.cs:513-544
+__device__ void pq_down_heap(TreeWork& w, int k)  // Trees.cs:513-544
 {
-    int v = w.heap[k];
+    const uint32_t v = w.hk[k];
     int j = k << 1;
     while (j <= w.heap_len) {
-        if (j < w.heap_len && node_smaller(tree, w.heap[j + 1], w.heap[j], w.depth)) j++;
-        if (node_smaller(tree, v, w.heap[j], w.depth)) break;
-        w.heap[k] = w.heap[j];
+        uint32_t e = w.hk[j];
+        if (j < w.heap_len) {
+            const uint32_t e2 = w.hk[j + 1];
+            if ((e2 >> 10) <= (e >> 10)) { j++; e = e2; }
+        }
+        if ((v >> 10) <= (e >> 10)) break;
+        w.hk[k] = e;
         k = j;
         j <<= 1;
     }
-    w.heap[k] = (uint16_t)v;
+    w.hk[k] = v;
 }
 
 // Trees.cs:404-501 (Build_tree) + 999-1109 (Gen_bitlen) + 1123-1151 (Gen_codes), run by one thread.
@@ -75,36 +80,38 @@ __device__ int build_tree(TreeWork& w, CodeData* tree, int kind)
     w.heap_max = HEAP_SIZE;
     for (n = 0; n < elems; n++) {
         if (tree[n].fc != 0) {
-            w.heap[++w.heap_len] = (uint16_t)(max_code = n);
-            w.depth[n] = 0;
+            w.hk[++w.heap_len] = heap_entry(tree[n].fc, 0, max_code = n);
         } else {
             tree[n].dl = 0;
         }
     }
     while (w.heap_len < 2) {  // Trees.cs:439-455: force two codes
         node = max_code < 2 ? ++max_code : 0;
-        w.heap[++w.heap_len] = (uint16_t)node;
+        w.hk[++w.heap_len] = heap_entry(1, 0, node);
         tree[node].fc = 1;
-        w.depth[node] = 0;
         w.opt_len--;
         if (has_stree) w.static_len -= tree_static_len(kind, node);
     }
-    for (n = w.heap_len / 2; n >= 1; n--) pq_down_heap(w, tree, n);
+    for (n = w.heap_len / 2; n >= 1; n--) pq_down_heap(w, n);
     node = elems;
     do {
-        n = w.heap[1];
-        w.heap[1] = w.heap[w.heap_len--];
-        pq_down_heap(w, tree, 1);
-        m = w.heap[1];
+        const uint32_t en = w.hk[1];
+        w.hk[1] = w.hk[w.heap_len--];
+        pq_down_heap(w, 1);
+        const uint32_t em = w.hk[1];
+        n = (int)(en & 1023u);
+        m = (int)(em & 1023u);
         w.heap[--w.heap_max] = (uint16_t)n;
         w.heap[--w.heap_max] = (uint16_t)m;
-        tree[node].fc = (uint16_t)(tree[n].fc + tree[m].fc);
-        w.depth[node] = (uint8_t)((w.depth[n] >= w.depth[m] ? w.depth[n] : w.depth[m]) + 1);
+        const uint32_t f = (en >> 18) + (em >> 18);
+        const uint32_t dn = (en >> 10) & 255u, dm = (em >> 10) & 255u;
+        tree[node].fc = (uint16_t)f;
         tree[n].dl = tree[m].dl = (uint16_t)node;
-        w.heap[1] = (uint16_t)node++;
-        pq_down_heap(w, tree, 1);
+        w.hk[1] = heap_entry(f, (dn >= dm ? dn : dm) + 1, node);
+        node++;
+        pq_down_heap(w, 1);
     } while (w.heap_len >= 2);
-    w.heap[--w.heap_max] = w.heap[1];
+    w.heap[--w.heap_max] = (uint16_t)(w.hk[1] & 1023u);
 
     // Gen_bitlen
     int h, bits, overflow = 0;

@@ -66,6 +66,8 @@ extern "C" {
 #define ZSB_SINGLE_STREAM 0x40u  /* the stream is ONE piece: written with FlushMode.NoFlush (one Write + Dispose), final block + Adler-32 */
 #define ZSB_SYNC_FLUSH 0x80u     /* deflate: every segment ends with FlushMode.SyncFlush, not FullFlush (the hash table is kept:
                                     one CTA compresses the segments in order; the stream inflates as ONE piece)               */
+#define ZSB_PARTIAL_FLUSH 0x100u /* deflate: every segment ends with FlushMode.PartialFlush (Tr_align; like ZSB_SYNC_FLUSH, and the
+                                    segments are not byte aligned: seg_end_offsets count the whole bytes written so far)      */
 #define ZSB_CONTINUATION 0x20u   /* inflate: `in` is a later shard of a stream (its first segment may open with a Q14 run) */
 
 typedef struct zsb_ctx zsb_ctx;

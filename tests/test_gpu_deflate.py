@@ -71,6 +71,20 @@ def test_sync_flush_segments(engine, oracle, corpus, level, strategy, ss):
     assert dec == data and ad == adler
 
 
+@pytest.mark.parametrize("level,strategy", [(1, 0), (3, 0), (6, 0), (9, 0), (6, 1), (6, 2), (6, 3), (1, 4)])
+@pytest.mark.parametrize("ss", [65536, 262144])
+def test_partial_flush_segments(engine, oracle, corpus, level, strategy, ss):
+    """SURVEY 8(f)-3, FlushMode.PartialFlush on every Write (Deflate.cs:566-581, Tr_align Trees.cs:658-680): one or two empty
+    static blocks instead of the stored marker, the stream not byte aligned between Writes, TotalOut = whole bytes so far."""
+    data = (corpus["alice29.txt"] + corpus["ptt5"] + corpus["alice29.txt"] + corpus["kennedy.xls"])[:5 * 262144 + 777]
+    want, want_ends = oracle.deflate_writes(data, ss, level, strategy, 0, flush_mode=1)
+    got, ends, adler = engine.deflate_segments(data, ss, level, strategy, partial_flush=True)
+    assert got == want and ends == want_ends and adler == zlib.adler32(data)
+    assert zlib.decompress(got) == data
+    dec, ad = engine.inflate_stream(got, len(data))
+    assert dec == data and ad == adler
+
+
 @pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7, 8, 9, -1])
 def test_every_level_matches_oracle(engine, oracle, corpus, level):
     data = corpus["lcet10.txt"] + corpus["sum"] + corpus["ptt5"][:200000]

@@ -29,14 +29,14 @@ class FakeEngine:
         self.fail_next = False
 
     def deflate_segments(self, data, seg_size, level, strategy=0, hash_variant=0, first_segment_index=0, halo=None, header=True,
-                         trailer=True, sync_flush=False):
+                         trailer=True, sync_flush=False, partial_flush=False):
         if self.fail_next:
             self.fail_next = False
             raise ZlibStreamException("deflating: device lost")
         data = bytes(data)
         self.calls.append(("deflate", len(data) // seg_size, first_segment_index, sync_flush))
-        if sync_flush:
-            out, ends = self.orc.deflate_writes(data, seg_size, level, strategy, hash_variant, flush_mode=2)
+        if sync_flush or partial_flush:
+            out, ends = self.orc.deflate_writes(data, seg_size, level, strategy, hash_variant, flush_mode=2 if sync_flush else 1)
             return out, ends, zlib.adler32(data) & 0xFFFFFFFF
         if first_segment_index == 0:
             stream, ends, ad = self.orc.deflate_segments(data, seg_size, level, strategy, hash_variant)
@@ -147,11 +147,16 @@ def test_sync_flush_goes_out_in_one_call():
     assert sink.getvalue() == want and z.SegmentEndOffsets == want_ends and zlib.decompress(want) == data
 
 
-def test_partial_flush_is_refused_and_level0_trailer():
+def test_partial_flush_and_level0_trailer():
     eng = FakeEngine()
-    z = ZlibOutputStream(io.BytesIO(), _opts(6, FlushMode.PartialFlush), engine=eng)
-    with pytest.raises(ZlibStreamException, match="deflating: .*PartialFlush"):
-        z.write(b"x" * SEG)
+    data = corpus_data.text_like(3 * SEG + 5, seed=8)
+    sink = io.BytesIO()
+    z = ZlibOutputStream(sink, _opts(6, FlushMode.PartialFlush), engine=eng)
+    for off in range(0, len(data), SEG):
+        z.write(data[off:off + SEG])
+    z.close()
+    want, want_ends = eng.orc.deflate_writes(data, SEG, 6, 0, 0, flush_mode=1)
+    assert sink.getvalue() == want and z.SegmentEndOffsets == want_ends and zlib.decompress(want) == data
     sink = io.BytesIO()
     z = ZlibOutputStream(sink, _opts(0, FlushMode.FullFlush), engine=eng)
     data = corpus_data.text_like(2 * SEG, seed=2)

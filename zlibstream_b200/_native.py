@@ -13,6 +13,7 @@ ZSB_OFFSETS_DEVICE = 0x10
 ZSB_CONTINUATION = 0x20
 ZSB_SINGLE_STREAM = 0x40
 ZSB_SYNC_FLUSH = 0x80
+ZSB_PARTIAL_FLUSH = 0x100
 
 # every symbol include/zsb200.h declares
 EXPORTS = [

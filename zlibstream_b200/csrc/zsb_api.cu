@@ -179,7 +179,7 @@ void timing_collect(zsb_ctx* c)
 }
 
 __global__ void finalize_stream_kernel(uint8_t* out, size_t out_cap, uint64_t* total_out, const uint32_t* adler,
-                                       int write_header, uint32_t header, int write_trailer, int* status)
+                                       int write_header, uint32_t header, int write_trailer, int* status, const uint64_t* total_bits)
 {
     // zlib header (Deflate.cs:464-493) and, for Finish, the final empty static block `03 00` followed by the
     // big-endian Adler-32 (Deflate.cs:627-635)
@@ -187,6 +187,23 @@ __global__ void finalize_stream_kernel(uint8_t* out, size_t out_cap, uint64_t* t
     if (write_header) {
         out[0] = (uint8_t)(header >> 8);
         out[1] = (uint8_t)header;
+    }
+    if (write_trailer == 4) {
+        // FlushMode.PartialFlush: the stream stands in the middle of a byte.  The final empty static block (BFINAL 1, type 01,
+        // END_BLOCK = 7 zero bits: the 10-bit value 3) goes in at the bit position, Bi_windup pads, then the Adler-32.
+        const uint64_t bits = *total_bits;
+        const uint64_t end = (bits + 10 + 7) >> 3;
+        if (end + 4 > out_cap) { *status = ZSB_BUF_ERROR; *total_out = end + 4; return; }
+        const uint32_t v = 3u << (bits & 7);
+        out[bits >> 3] |= (uint8_t)v;
+        out[(bits >> 3) + 1] |= (uint8_t)(v >> 8);
+        const uint32_t a = *adler;
+        out[end] = (uint8_t)(a >> 24);
+        out[end + 1] = (uint8_t)(a >> 16);
+        out[end + 2] = (uint8_t)(a >> 8);
+        out[end + 3] = (uint8_t)a;
+        *total_out = end + 4;
+        return;
     }
     if (write_trailer) {   // 1: `03 00` + Adler-32; 2: the final block is already in the stream (one-piece stream), Adler-32 only;
                            // 3: level 0, the final block is an empty STORED block `01 00 00 FF FF` (Deflate.Stored.cs:80 with eof)
@@ -612,9 +629,12 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     // FlushMode.SyncFlush on every Write (Deflate.cs:583-595): the same marker as a full flush, but the hash table is kept, so
     // a segment may refer to the 32 KiB before it.  Segments are then neither independent work (one CTA parses them in
     // order; HuffmanOnly and Rle, which never read the hash table, keep their parallel path) nor independently decodable.
-    const bool sync_flush = (flags & ZSB_SYNC_FLUSH) != 0;
-    if (sync_flush && (single || first_segment_index != 0 || level == 0))
-        return fail(ctx, ZSB_STREAM_ERROR, "ZSB_SYNC_FLUSH needs the whole stream in one call, level >= 1");
+    // FlushMode.PartialFlush (Deflate.cs:566-581): Tr_align (one or two empty static blocks, Trees.cs:658-680) instead of the
+    // stored marker; the hash table is kept as for a sync flush and the stream is not even byte aligned between Writes.
+    const bool partial_flush = (flags & ZSB_PARTIAL_FLUSH) != 0;
+    const bool sync_flush = (flags & ZSB_SYNC_FLUSH) != 0 || partial_flush;
+    if (sync_flush && (single || first_segment_index != 0 || level == 0 || (flags & ZSB_NO_HEADER)))
+        return fail(ctx, ZSB_STREAM_ERROR, "ZSB_SYNC_FLUSH / ZSB_PARTIAL_FLUSH need the whole stream in one call (header included), level >= 1");
     if (single) {
         if (n > (64u << 20)) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream holds at most 64 MiB on the device path");
         if (first_segment_index != 0) return fail(ctx, ZSB_STREAM_ERROR, "a one-piece stream starts at segment 0");
@@ -718,6 +738,10 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     // Host buffers: a few batches, so that the upload of batch b + 1 and the download of batch b - 1's output run beside the
     // kernels of batch b.  Batches are whole multiples of the SM count (the LZ77 kernels hand out one segment per SM at a time).
     if (sync_flush && batch < nseg) return fail(ctx, ZSB_MEM_ERROR, "ZSB_SYNC_FLUSH: the stream does not fit one batch of scratch");
+    if (partial_flush) {   // segments share their edge bytes: the packer ORs those into a zeroed buffer
+        const size_t zb = std::min(out_cap, zsb_deflate_bound(n, seg_size));
+        CU(cudaMemsetAsync(d_out, 0, zb, st));
+    }
     bool piped = false;
     if ((host_in || host_out) && nseg >= (size_t)ctx->num_sms * 16 && !sync_flush) {
         size_t pb = (nseg + 3) / 4;
@@ -808,6 +832,8 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         H.out_cap = out_cap;
         H.status = d_status;
         H.finish_mode = single ? 1 : 0;
+        H.partial_flush = partial_flush ? 1 : 0;
+        H.total_bits = reinterpret_cast<uint64_t*>(small + 32);
         H.level0 = level0 ? 1 : 0;
         timing_mark(ctx, 1, true);
         CU(launch_block_trees(H, st));
@@ -845,7 +871,8 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     header |= level_flags << 6;
     header += 31 - (header % 31);
     finalize_stream_kernel<<<1, 1, 0, st>>>(d_out, out_cap, d_total, d_adler, write_header ? 1 : 0, header,
-                                            write_trailer ? ((single && nseg) ? 2 : (level0 ? 3 : 1)) : 0, d_status);
+                                            write_trailer ? ((single && nseg) ? 2 : (level0 ? 3 : ((partial_flush && nseg) ? 4 : 1))) : 0, d_status,
+                                            reinterpret_cast<const uint64_t*>(small + 32));
     CU(cudaGetLastError());
     ctx->launches++;
 

@@ -279,14 +279,26 @@ __global__ void __launch_bounds__(BT_THREADS) block_trees_kernel(HuffParams P)
     for (int i = tid; i < kHdrWords; i += BT_THREADS) sm.hdr[i] = 0;
     __syncthreads();
     // Tr_tally_* frequency counts (Deflate.cs:922-923,945) as a shared-memory histogram
-    for (int i = tid; i < nsym; i += BT_THREADS) {
-        uint32_t s = sym[i];
-        uint32_t dist = s & 0xFFFF, lc = s >> 16;
-        if (dist == 0) {
-            atomicAdd(&sm.lfreq[lc], 1u);
-        } else {
-            atomicAdd(&sm.lfreq[length_code_of((int)lc) + LITERALS + 1], 1u);
-            atomicAdd(&sm.dfreq[dist_code_of((int)dist - 1)], 1u);
+    // eight loads in flight per thread: one load per trip left every warp waiting a full HBM round trip 128 times
+    constexpr int HU = 8;
+    for (int base = 0; base < nsym; base += BT_THREADS * HU) {
+        uint32_t v[HU];
+#pragma unroll
+        for (int k = 0; k < HU; k++) {
+            const int i = base + k * BT_THREADS + tid;
+            v[k] = i < nsym ? __ldg(sym + i) : 0xFFFFFFFFu;   // no symbol has lc > 255
+        }
+#pragma unroll
+        for (int k = 0; k < HU; k++) {
+            const uint32_t s = v[k];
+            if (s == 0xFFFFFFFFu) continue;
+            const uint32_t dist = s & 0xFFFF, lc = s >> 16;
+            if (dist == 0) {
+                atomicAdd(&sm.lfreq[lc], 1u);
+            } else {
+                atomicAdd(&sm.lfreq[length_code_of((int)lc) + LITERALS + 1], 1u);
+                atomicAdd(&sm.dfreq[dist_code_of((int)dist - 1)], 1u);
+            }
         }
     }
     __syncthreads();
@@ -412,10 +424,83 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(HuffParams P)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = *P.total_out;  // bytes already in `out`: header, earlier batches
     __syncthreads();
+    if (P.partial_flush) {
+        // FlushMode.PartialFlush (Deflate.cs:566-581, Trees.cs:658-680): every Write ends with Tr_align -- an empty static
+        // block, and a second one if the inflater could not yet see the end of the last real block -- instead of the stored
+        // marker.  Nothing aligns the stream to a byte, so a segment starts where the previous one stopped, bit for bit: one
+        // thread walks the segments in order.  TotalOut after a Write counts the whole bytes that have left (Bi_flush).
+        if (tid == 0) {
+            uint64_t stream_bits = carry_s * 8;   // header bytes of this call (2) are already in `out`
+            for (uint32_t seg = 0; seg < P.nseg; seg++) {
+                BlockRec* blocks = P.blocks + (size_t)seg * P.max_blocks;
+                const uint32_t nb = P.nblocks[seg];
+                SegLayout lay;
+                lay.out_offset = stream_bits >> 3;
+                lay.bit_shift = (uint32_t)(stream_bits & 7);
+                lay.pad_ = 0;
+                Drain dr;
+                dr.a = (P.first_seg_index + seg == 0) ? CHUNK_OUT - 2 : CHUNK_OUT;
+                dr.accounted = 0;
+                uint64_t bitpos = lay.bit_shift;   // relative to the first bit of byte out_offset
+                bool drained = false;
+                int last_eob_len = 8;
+                for (uint32_t b = 0; b < nb; b++) {
+                    BlockRec& r = blocks[b];
+                    r.bit_offset = bitpos - lay.bit_shift;
+                    if (r.type == BT_STORED) {
+                        bitpos = ((bitpos + 3 + 7) & ~7ull) + 32 + 8ull * r.in_len;
+                        last_eob_len = 8;
+                    } else {
+                        bitpos += 3 + r.hdr_bits + r.body_bits;
+                        last_eob_len = r.type == BT_STATIC ? 7 : (int)(P.codes[(size_t)seg * P.max_blocks + b].lcode[END_BLOCK] >> 16);
+                    }
+                    drained = dr.step(bitpos);
+                }
+                TailSink t;
+                for (int i = 0; i < kTailWords; i++) t.w[i] = 0;
+                t.nbits = 0;
+                const uint64_t tail_start = bitpos;
+                auto empty_static = [&]() {
+                    t.put(0x2u, 3);
+                    t.put(0u, 7);
+                    bitpos += 10;
+                };
+                while (drained) {      // the flush re-run with nothing to compress: an empty static block
+                    empty_static();
+                    last_eob_len = 7;
+                    drained = dr.step(bitpos);
+                }
+                for (;;) {
+                    empty_static();    // Tr_align; bi_valid after Bi_flush = the bits of the unfinished byte
+                    if (1 + last_eob_len + 10 - (int)(bitpos & 7) < 9) empty_static();
+                    last_eob_len = 7;
+                    drained = dr.step(bitpos);
+                    if (!drained) break;
+                    do {
+                        empty_static();
+                        drained = dr.step(bitpos);
+                    } while (drained);
+                }
+                lay.out_bytes = (uint32_t)(((bitpos + 7) >> 3));   // bytes this segment touches, the shared last one included
+                lay.tail_nbits = t.nbits;
+                lay.tail_bit_offset = tail_start - lay.bit_shift;
+                for (int i = 0; i < kTailWords; i++) lay.tail[i] = t.w[i];
+                P.layout[seg] = lay;
+                stream_bits = lay.out_offset * 8 + bitpos;
+                if (P.seg_end) P.seg_end[seg] = stream_bits >> 3;
+            }
+            *P.total_out = (stream_bits + 7) >> 3;
+            if (P.total_bits) *P.total_bits = stream_bits;
+            if (((stream_bits + 7) >> 3) > P.out_cap) *P.status = -5;  // ZSB_BUF_ERROR
+        }
+        return;
+    }
     for (uint32_t base = 0; base < P.nseg; base += LAYOUT_THREADS) {
         const uint32_t seg = base + tid;
         uint64_t bytes = 0;
         SegLayout lay;
+        lay.bit_shift = 0;
+        lay.pad_ = 0;
         if (seg < P.nseg) {
             BlockRec* blocks = P.blocks + (size_t)seg * P.max_blocks;
             const uint32_t nb = P.nblocks[seg];
@@ -545,6 +630,7 @@ struct Packer {
     uint64_t seg_byte_end;   // one past the last
     uint64_t stage_word0;    // global 32-bit word index that stage[0] maps to
     uint64_t bitpos;         // next free bit, absolute (global byte offset * 8 + bit)
+    bool shared_edges;       // FlushMode.PartialFlush: the first and the last byte may hold a neighbour's bits too (OR them in)
 
     __device__ __forceinline__ void or_bits(uint64_t at, uint64_t value, int len)
     {
@@ -568,7 +654,19 @@ struct Packer {
             const uint64_t gw = stage_word0 + i;
             const uint64_t b0 = gw * 4;
             const uint32_t v = sm->stage[i];
-            if (b0 >= seg_byte0 && b0 + 4 <= seg_byte_end) {
+            if (shared_edges) {
+                // the output was zeroed; a word that holds the segment's first or last byte is merged, the others are stored
+                if (b0 > seg_byte0 && b0 + 4 < seg_byte_end) {
+                    *reinterpret_cast<uint32_t*>(out + b0) = v;
+                } else {
+                    uint32_t m = 0;
+                    for (int k = 0; k < 4; k++) {
+                        const uint64_t b = b0 + k;
+                        if (b >= seg_byte0 && b < seg_byte_end) m |= 0xFFu << (8 * k);
+                    }
+                    if (v & m) atomicOr(reinterpret_cast<uint32_t*>(out + b0), v & m);
+                }
+            } else if (b0 >= seg_byte0 && b0 + 4 <= seg_byte_end) {
                 *reinterpret_cast<uint32_t*>(out + b0) = v;
             } else {
                 for (int k = 0; k < 4; k++) {
@@ -609,11 +707,12 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(HuffParams P)
     pk.out = P.out;
     pk.seg_byte0 = lay.out_offset;
     pk.seg_byte_end = lay.out_offset + lay.out_bytes;
-    pk.bitpos = lay.out_offset * 8;
+    pk.bitpos = lay.out_offset * 8 + lay.bit_shift;
     pk.stage_word0 = pk.bitpos >> 5;
+    pk.shared_edges = P.partial_flush != 0;
     for (uint32_t i = tid; i < PK_STAGE_WORDS + 4; i += PK_THREADS) sm.stage[i] = 0;
     __syncthreads();
-    const uint64_t seg_bit0 = lay.out_offset * 8;
+    const uint64_t seg_bit0 = lay.out_offset * 8 + lay.bit_shift;
 
     for (uint32_t b = 0; b < nb; b++) {
         const BlockRec& r = blocks[b];
@@ -657,18 +756,32 @@ __global__ void __launch_bounds__(PK_THREADS) pack_kernel(HuffParams P)
         // symbols, PK_CHUNK at a time: Compress_block (Trees.cs:956-989) with the bit offsets from a prefix sum
         const uint32_t* sym = seg_sym + r.sym_begin;
         const uint32_t nsym = r.sym_count;
+        // the symbols of the NEXT chunk are loaded while this one is packed (one HBM round trip per chunk otherwise)
+        uint32_t nxt[PK_SYMS_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < PK_SYMS_PER_THREAD; k++) {
+            const uint32_t i = tid * PK_SYMS_PER_THREAD + k;
+            nxt[k] = i < nsym ? __ldg(sym + i) : 0u;
+        }
         for (uint32_t c0 = 0; c0 < nsym; c0 += PK_CHUNK) {
             if (pk.stage_bits_free() < (uint64_t)PK_CHUNK * 48 + 64) pk.flush(false);
             uint64_t bits[PK_SYMS_PER_THREAD];
             int lens[PK_SYMS_PER_THREAD];
             uint32_t total = 0;
+            uint32_t cur_s[PK_SYMS_PER_THREAD];
+#pragma unroll
+            for (int k = 0; k < PK_SYMS_PER_THREAD; k++) {
+                cur_s[k] = nxt[k];
+                const uint32_t i2 = c0 + PK_CHUNK + tid * PK_SYMS_PER_THREAD + k;
+                nxt[k] = i2 < nsym ? __ldg(sym + i2) : 0u;
+            }
 #pragma unroll
             for (int k = 0; k < PK_SYMS_PER_THREAD; k++) {
                 const uint32_t i = c0 + tid * PK_SYMS_PER_THREAD + k;
                 bits[k] = 0;
                 lens[k] = 0;
                 if (i < nsym) {
-                    const uint32_t s = sym[i];
+                    const uint32_t s = cur_s[k];
                     const uint32_t dist = s & 0xFFFF, lc = s >> 16;
                     if (dist == 0) {
                         const uint32_t e = sm.lcode[lc];

@@ -59,6 +59,8 @@ struct SegLayout {
     uint32_t tail_nbits;
     uint64_t tail_bit_offset;       // relative to the segment's first output bit
     uint32_t tail[kTailWords];      // LSB-first bits
+    uint32_t bit_shift;             // FlushMode.PartialFlush: the segment starts this many bits into its first byte (else 0)
+    uint32_t pad_;
 };
 
 struct HuffParams {
@@ -81,6 +83,8 @@ struct HuffParams {
     uint8_t* out;
     size_t out_cap;
     int* status;              // device int: set to ZSB_BUF_ERROR if out_cap is too small
+    int partial_flush = 0;    // FlushMode.PartialFlush: Tr_align instead of the stored marker; segments are not byte aligned
+    uint64_t* total_bits = nullptr;   // partial_flush: device scalar, the stream's bit position after the last segment
     int level0 = 0;           // level 0: every block is stored (Trees.cs:586-594 with level == 0), also the empty ones of Q10
     int finish_mode = 0;      // 1: one Write with FlushMode.NoFlush, then Finish: the last block carries BFINAL, no flush marker
 };

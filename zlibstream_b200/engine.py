@@ -91,7 +91,7 @@ class Engine:
     # -- host-buffer API --------------------------------------------------------------------------
     def deflate_segments(self, data, seg_size: int, level: int, strategy: int = 0,
                          hash_variant: int = HashVariant.Crc32C, first_segment_index: int = 0, halo=None,
-                         header: bool = True, trailer: bool = True, sync_flush: bool = False):
+                         header: bool = True, trailer: bool = True, sync_flush: bool = False, partial_flush: bool = False):
         """Returns (compressed bytes, list of segment end offsets, adler32 of data).  sync_flush: every Write ends with
         FlushMode.SyncFlush instead of FullFlush (segments share the hash table: serial on the device, one-piece to inflate)."""
         addr, n, keep = _addr(data)
@@ -103,6 +103,7 @@ class Engine:
         adler = ctypes.c_uint32(0)
         flags = (0 if header else _native.ZSB_NO_HEADER) | (0 if trailer else _native.ZSB_NO_TRAILER)
         flags |= _native.ZSB_SYNC_FLUSH if sync_flush else 0
+        flags |= _native.ZSB_PARTIAL_FLUSH if partial_flush else 0
         haddr, hkeep = 0, None
         if halo is not None:
             haddr, hn, hkeep = _addr(halo)

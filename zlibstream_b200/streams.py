@@ -7,12 +7,12 @@ Writing.  One `Write` with `Options.FlushMode == FullFlush` is one segment (Zlib
 segment gives a GPU nothing to parallelise, segments are staged in ONE buffer and submitted in batches (SURVEY section 8b
 "host-side batching"): compressed bytes reach BaseStream in order when a batch completes, on Flush() and on Dispose().
   * FullFlush  equally sized writes (a multiple of 32 KiB, >= 64 KiB; the last write may be shorter), batched.
-  * SyncFlush  the same writes, but the hash table survives the flush (Deflate.cs:583-595): the segments of the whole
-               stream go to the device in one call at Dispose and are parsed one after the other.
+  * SyncFlush, PartialFlush  the same writes, but the hash table survives the flush (Deflate.cs:566-595; a partial flush
+               ends with Tr_align instead of the stored marker and does not even align the stream to a byte): the segments of the
+               whole stream go to the device in one call at Dispose and are parsed one after the other.
   * NoFlush    everything written is compressed as ONE Write at Dispose (the reference's benchmark call pattern,
                DeflateCorpusBenchmark.cs:86-99).  The reference's output depends on where its Write calls fall even without a
                flush, so the bytes equal the reference's for a caller that makes one Write; at most 64 MiB.
-  * PartialFlush is not built.
 
 Reading.  ZlibInputStream reads ahead a bounded batch of compressed bytes from BaseStream, finds the segments in it (from
 the side-car offsets, or by the full-flush markers: zsb_build_segment_index), decodes the batch on the device and serves
@@ -126,8 +126,6 @@ class ZlibOutputStream(io.RawIOBase):
         if self._finished or self._failed:
             raise ZlibStreamException("deflating: stream error")
         mode = self.Options.FlushMode
-        if mode == FlushMode.PartialFlush:
-            raise ZlibStreamException("deflating: FlushMode.PartialFlush is not built on the device path (no CPU fallback)")
         if mode == FlushMode.NoFlush:
             if len(self._stage) + n > (64 << 20):
                 raise ZlibStreamException("deflating: a stream without flushes holds at most 64 MiB on the device path")
@@ -198,9 +196,10 @@ class ZlibOutputStream(io.RawIOBase):
                 self._emit(comp, [], adler, len(self._stage))
                 self._stage = bytearray()
                 self._finished = True
-            elif mode == FlushMode.SyncFlush and self._stage:
+            elif mode in (FlushMode.SyncFlush, FlushMode.PartialFlush) and self._stage:
                 comp, ends, adler = self._engine.deflate_segments(self._stage, self._seg_size, self._level, strategy,
-                                                                  int(self._hash), sync_flush=True)
+                                                                  int(self._hash), sync_flush=mode == FlushMode.SyncFlush,
+                                                                  partial_flush=mode == FlushMode.PartialFlush)
                 self._emit(comp, ends, adler, len(self._stage))     # header, segments and trailer in one piece
                 self._stage = bytearray()
                 self._finished = True

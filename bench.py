@@ -413,7 +413,7 @@ def bench_deflate(c):
 
     e2e = None
     if not args.no_e2e:
-        e2e = e2e_deflate(c, data, n, cap)
+        e2e = e2e_deflate(c, data, n, cap, out, res.local_len)
 
     if c.rank != 0:
         return None
@@ -571,7 +571,7 @@ def inflate_large(c, inflate, data, out, comp_len, seg_end, nseg, ratio):
         del big, big_dec, big_ends
 
 
-def e2e_deflate(c, data, n, cap):
+def e2e_deflate(c, data, n, cap, dev_out, dev_len):
     import ctypes
     import torch
     from zlibstream_b200 import _native
@@ -606,9 +606,10 @@ def e2e_deflate(c, data, n, cap):
     c.barrier()
     ms = max_over_ranks(c, max(e0.elapsed_time(e1), 0.0))
     wall = (time.perf_counter() - t0) * 1e3
+    same = int(out_len.value) == dev_len and bool(torch.equal(h_out[:dev_len], dev_out[:dev_len].cpu()))
     return {"value": n * c.world * steps / (ms / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n,
             "d2h_bytes_per_step": int(out_len.value) + 8 * nseg + 16, "ms_per_step": ms / steps, "wall_ms_per_step": wall / steps,
-            "api": "zsb_deflate_segments with pinned host buffers"}
+            "api": "zsb_deflate_segments with pinned host buffers", "bytes_equal_device_path": same}
 
 
 def run_config(c, name, d, level, strategy, seg, parity_mib=0):

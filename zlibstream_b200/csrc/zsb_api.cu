@@ -175,6 +175,8 @@ void timing_collect(zsb_ctx* c)
             c->ms[4] += b;
         }
     }
+    if (c->ms[0] == 0 && c->ms[3] + c->ms[4] > 0) c->ms[0] = c->ms[3] + c->ms[4];
+    else if (c->ev_mid.empty() && c->ms[3] + c->ms[4] > 0) c->ms[0] += c->ms[3] + c->ms[4];   // + a short last segment's kernel
     c->ms_valid = true;
 }
 
@@ -743,17 +745,32 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         CU(cudaMemsetAsync(d_out, 0, zb, st));
     }
     bool piped = false;
+    const size_t scratch_batch = batch;   // segments the scratch budget allows at once
+    size_t first_batch = 0;   // piped: the first batch may be smaller than the others (0 = no)
     if ((host_in || host_out) && nseg >= (size_t)ctx->num_sms * 16 && !sync_flush) {
-        size_t pb = (nseg + 3) / 4;
-        pb = (pb + ctx->num_sms - 1) / ctx->num_sms * ctx->num_sms;
-        if (pb < batch) batch = pb;
+        // about four batches.  Level 1: the resolve kernel parses one segment per warp, 32 warps per SM, so a batch is a whole
+        // number of those waves (4096 segments on 4736 warp slots cost a full wave each: 45 -> 56 ms per GiB); what is left over
+        // goes FIRST, so that the kernels start after the shortest upload.  Other levels: a multiple of the SM count.
+        const size_t unit = use_lists ? (size_t)ctx->num_sms * 32 : (size_t)ctx->num_sms;
+        const size_t nb_target = env_size("ZSB_PIPE_BATCHES", 4);
+        size_t k = (nseg / unit + nb_target - 1) / nb_target;
+        if (k < 1) k = 1;
+        size_t pb = k * unit;
+        if (pb < batch) {
+            batch = pb;
+            first_batch = nseg % batch;
+        }
         piped = (nseg + batch - 1) / batch <= (size_t)zsb_ctx::kMaxPipe;
+        if (!piped) first_batch = 0;
     }
+    auto batch_len = [&](size_t s0) { return (s0 == 0 && first_batch) ? first_batch : batch; };
+    const bool split_ab = piped && use_lists && scratch_batch >= nseg;   // scratch (records, symbols) for every segment of the call
+    const size_t scratch_segs = split_ab ? nseg : batch;
     if (host_in) {
         if (piped) {
             int b = 0;
-            for (size_t s0 = 0; s0 < nseg; s0 += batch, b++) {
-                const size_t off = s0 * seg_size, len = std::min(n - off, batch * seg_size);
+            for (size_t s0 = 0; s0 < nseg; s0 += batch_len(s0), b++) {
+                const size_t off = s0 * seg_size, len = std::min(n - off, batch_len(s0) * seg_size);
                 CU(cudaMemcpyAsync(ctx->in_stage.as<uint8_t>() + off, reinterpret_cast<const uint8_t*>(in) + off, len, cudaMemcpyHostToDevice, ctx->copy_stream));
                 CU(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
             }
@@ -762,18 +779,16 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
     const uint64_t hdr_bytes = write_header ? 2u : 0u;
     uint64_t copied_to = hdr_bytes;   // host output bytes [hdr_bytes, copied_to) are already on their way
     if (nseg) {
-        CU(ctx->sym.reserve(batch * sym_bytes_per_seg));
-        if (use_lists) CU(ctx->lists.reserve(batch * list_bytes_per_seg));
-        CU(ctx->blocks.reserve(batch * max_blocks * sizeof(BlockRec)));
-        CU(ctx->codes.reserve(batch * max_blocks * sizeof(BlockCodesDev)));
-        CU(ctx->nblocks.reserve(batch * sizeof(uint32_t)));
-        CU(ctx->layout.reserve(batch * sizeof(SegLayout)));
+        CU(ctx->sym.reserve(scratch_segs * sym_bytes_per_seg));
+        if (use_lists) CU(ctx->lists.reserve(scratch_segs * list_bytes_per_seg));
+        CU(ctx->blocks.reserve(scratch_segs * max_blocks * sizeof(BlockRec)));
+        CU(ctx->codes.reserve(scratch_segs * max_blocks * sizeof(BlockCodesDev)));
+        CU(ctx->nblocks.reserve(scratch_segs * sizeof(uint32_t)));
+        CU(ctx->layout.reserve(scratch_segs * sizeof(SegLayout)));
     }
 
-    int bidx = 0;
-    for (size_t s0 = 0; s0 < nseg; s0 += batch, bidx++) {
-        const uint32_t cnt = (uint32_t)((nseg - s0) < batch ? (nseg - s0) : batch);
-        if (piped && host_in) CU(cudaStreamWaitEvent(st, ctx->ev_in[bidx], 0));
+    // scratch_seg0 = index of segment s0 inside the scratch arrays: 0 when every batch reuses them, s0 when they hold the whole call
+    auto lz_params = [&](size_t s0, uint32_t cnt, size_t scratch_seg0) {
         Lz77Params L;
         L.in = d_in + s0 * seg_size;
         L.n = n - s0 * seg_size;
@@ -787,30 +802,22 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         L.hash_variant = hash_variant;
         L.good = cfg.good; L.lazy = cfg.lazy; L.nice = cfg.nice; L.chain = cfg.chain;
         L.fn = strategy == ZSB_RLE ? FN_RLE : cfg.fn;
-        L.sym = ctx->sym.as<uint32_t>();
+        L.sym = ctx->sym.as<uint32_t>() + scratch_seg0 * seg_size;
         L.sym_stride = seg_size;
-        L.blocks = ctx->blocks.as<BlockRec>();
+        L.blocks = ctx->blocks.as<BlockRec>() + scratch_seg0 * max_blocks;
         L.max_blocks = max_blocks;
-        L.nblocks = ctx->nblocks.as<uint32_t>();
+        L.nblocks = ctx->nblocks.as<uint32_t>() + scratch_seg0;
         L.seg_adler = ctx->seg_adler.as<uint2>() + s0;
         L.work_counter = d_work;
         L.crc_tab = ctx->crc_tab;
         L.stats = ctx->lz_stats;
-        L.lists = use_lists ? ctx->lists.as<uint4>() : nullptr;
+        L.lists = use_lists ? ctx->lists.as<uint4>() + scratch_seg0 * seg_size * 2 : nullptr;
         L.chained = sync_flush ? 1 : 0;
-        CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
-        timing_mark(ctx, 0, true);
-        if (use_lists) {   // an event between the two level-1 kernels: their times are reported apart
-            cudaEvent_t mid;
-            CU(cudaEventCreate(&mid));
-            ctx->ev_mid.push_back(mid);
-            ctx->ev_mid_of.push_back((int)ctx->ev.size() - 1);
-            L.ev_mid = mid;
-        }
-        CU(launch_lz77(L, ctx->num_sms, st));
-        timing_mark(ctx, 0, false);
-        ctx->launches++;
-
+        return L;
+    };
+    int bidx = 0;
+    auto huffman_stage = [&](size_t s0, uint32_t cnt, size_t scratch_seg0) -> int {
+        const Lz77Params L = lz_params(s0, cnt, scratch_seg0);
         HuffParams H;
         H.in = L.in;
         H.n = L.n;
@@ -823,8 +830,8 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         H.blocks = L.blocks;
         H.max_blocks = max_blocks;
         H.nblocks = L.nblocks;
-        H.codes = ctx->codes.as<BlockCodesDev>();
-        H.layout = ctx->layout.as<SegLayout>();
+        H.codes = ctx->codes.as<BlockCodesDev>() + scratch_seg0 * max_blocks;
+        H.layout = ctx->layout.as<SegLayout>() + scratch_seg0;
         H.out_base = 0;  // layout_kernel reads the running total from *total_out
         H.total_out = d_total;
         H.seg_end = d_seg_end ? d_seg_end + s0 : nullptr;
@@ -855,6 +862,67 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
                 }
             }
         }
+        return ZSB_OK;
+    };
+
+    if (split_ab) {
+        // Level 1 with host buffers and scratch for the whole call: the list kernel runs piece by piece behind the uploads, the
+        // parse runs ONCE over every segment (cutting it into batches costs a partly filled wave of warps per batch: 45 -> 52
+        // ms per GiB), the Huffman stage runs piece by piece in front of the downloads.
+        const size_t nfull = std::min(nseg, n / seg_size);   // a short last segment takes the one-kernel path
+        for (size_t s0 = 0; s0 < nseg; s0 += batch_len(s0), bidx++) {
+            const size_t e0 = std::min(nfull, s0 + batch_len(s0));
+            if (host_in) CU(cudaStreamWaitEvent(st, ctx->ev_in[bidx], 0));
+            if (e0 <= s0) continue;
+            Lz77Params L = lz_params(s0, (uint32_t)(e0 - s0), s0);
+            CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
+            timing_mark(ctx, 3, true);
+            CU(launch_lz77_lists(L, ctx->num_sms, st));
+            timing_mark(ctx, 3, false);
+            ctx->launches++;
+        }
+        if (nfull) {
+            Lz77Params L = lz_params(0, (uint32_t)nfull, 0);
+            CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
+            timing_mark(ctx, 4, true);
+            CU(launch_lz77_resolve(L, ctx->num_sms, st));
+            timing_mark(ctx, 4, false);
+            ctx->launches++;
+        }
+        if (nfull < nseg) {
+            Lz77Params T = lz_params(nfull, (uint32_t)(nseg - nfull), nfull);
+            T.lists = nullptr;
+            CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
+            timing_mark(ctx, 0, true);
+            CU(launch_lz77(T, ctx->num_sms, st));
+            timing_mark(ctx, 0, false);
+            ctx->launches++;
+        }
+        bidx = 0;
+        for (size_t s0 = 0; s0 < nseg; s0 += batch_len(s0), bidx++) {
+            const uint32_t cnt = (uint32_t)((nseg - s0) < batch_len(s0) ? (nseg - s0) : batch_len(s0));
+            int rc = huffman_stage(s0, cnt, s0);
+            if (rc != ZSB_OK) return rc;
+        }
+    } else
+    for (size_t s0 = 0; s0 < nseg; s0 += batch_len(s0), bidx++) {
+        const uint32_t cnt = (uint32_t)((nseg - s0) < batch_len(s0) ? (nseg - s0) : batch_len(s0));
+        if (piped && host_in) CU(cudaStreamWaitEvent(st, ctx->ev_in[bidx], 0));
+        Lz77Params L = lz_params(s0, cnt, 0);
+        CU(cudaMemsetAsync(d_work, 0, 3 * sizeof(unsigned int), st));
+        timing_mark(ctx, 0, true);
+        if (use_lists) {   // an event between the two level-1 kernels: their times are reported apart
+            cudaEvent_t mid;
+            CU(cudaEventCreate(&mid));
+            ctx->ev_mid.push_back(mid);
+            ctx->ev_mid_of.push_back((int)ctx->ev.size() - 1);
+            L.ev_mid = mid;
+        }
+        CU(launch_lz77(L, ctx->num_sms, st));
+        timing_mark(ctx, 0, false);
+        ctx->launches++;
+        int rc = huffman_stage(s0, cnt, 0);
+        if (rc != ZSB_OK) return rc;
     }
     // ---- Adler-32 of the whole input, header, trailer ----
     if (level0) {   // no LZ77 kernel has read the input: checksum it here (per 64 KiB chunk, then the same fold)

@@ -213,6 +213,23 @@ def test_stream_classes_other_flush_modes(engine, oracle, corpus):
     assert zi.read() == big and zi.Adler == adler and zi.TotalIn == len(full)
 
 
+@pytest.mark.parametrize("level,strategy", [(1, 0), (6, 3)])
+def test_piped_host_inflate_equals_the_input(engine, oracle, corpus, monkeypatch, level, strategy):
+    """Host buffers + side-car + many segments: uploads, kernels and downloads overlap over 2-4 batches (the threshold is
+    lowered here).  Rle: carried runs (Q14) cross the batch boundaries and the completed output is copied again."""
+    monkeypatch.setenv("ZSB_INFLATE_PIPE_SEGMENTS", "16")
+    ss = 65536
+    data = (corpus["ptt5"] + bytes(3 * ss) + corpus["alice29.txt"]) * 3 + b"z" * 1000
+    comp, ends, adler = oracle.deflate_segments_parallel(data, ss, level, strategy)
+    assert len(ends) >= 32
+    out, ad = engine.inflate_segments(comp, ends, ss, len(data))
+    assert out == data and ad == adler
+    bad = bytearray(comp)
+    bad[ends[len(ends) // 2] - 40] ^= 0x55
+    with pytest.raises(Exception, match="inflating: "):
+        engine.inflate_segments(bytes(bad), ends, ss, len(data))
+
+
 def test_stream_class_argument_behaviour(engine):
     from zlibstream_b200 import CompressionLevel, FlushMode, ZlibOptions, ZlibOutputStream, ZlibStreamException
     with pytest.raises(ValueError):

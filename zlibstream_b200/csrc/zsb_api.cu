@@ -1015,7 +1015,26 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     // ---- header checks on the host (Inflate.cs:120-178) need the first two bytes ----
     uint8_t hdr[2] = {0, 0};
     const uint8_t* d_in = reinterpret_cast<const uint8_t*>(in);
-    if (!(flags & ZSB_IN_DEVICE)) {
+    // Host buffers, a side-car and enough segments: the call is cut into up to 8 batches of >= 16384 segments (the lane kernel
+    // decodes one batch in the time the download of the previous one takes), the upload of batch b + 1 and the download of batch
+    // b - 1 run on the copy stream beside the kernel of batch b.  The download (1 / ratio times the upload) bounds the call.
+    const size_t pipe_min = env_size("ZSB_INFLATE_PIPE_SEGMENTS", 65536);   // tests lower it
+    const bool pipe_inf = !(flags & (ZSB_IN_DEVICE | ZSB_OUT_DEVICE | ZSB_OFFSETS_DEVICE)) && !single && seg_end_offsets && nseg >= pipe_min && nseg >= 2;
+    size_t pipe_per = 0;
+    if (pipe_inf) {
+        pipe_per = std::max<size_t>(std::max<size_t>(1, pipe_min / 4), (nseg + zsb_ctx::kMaxPipe - 1) / zsb_ctx::kMaxPipe);
+        CU(ctx->in_stage.reserve(n ? n : 1));
+        d_in = ctx->in_stage.as<uint8_t>();
+        if (n >= 2) memcpy(hdr, in, 2);
+        int b = 0;
+        for (size_t k0 = 0; k0 < nseg; k0 += pipe_per, b++) {
+            const size_t k1 = std::min(nseg, k0 + pipe_per);
+            const uint64_t c0 = k0 ? seg_end_offsets[k0 - 1] : 0, c1 = k1 == nseg ? n : seg_end_offsets[k1 - 1];
+            if (c1 > n || c0 > c1) return fail(ctx, ZSB_BUF_ERROR, "buffer error");
+            CU(cudaMemcpyAsync(ctx->in_stage.as<uint8_t>() + c0, reinterpret_cast<const uint8_t*>(in) + c0, c1 - c0, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+        }
+    } else if (!(flags & ZSB_IN_DEVICE)) {
         CU(ctx->in_stage.reserve(n ? n : 1));
         CU(cudaMemcpyAsync(ctx->in_stage.p, in, n, cudaMemcpyHostToDevice, st));
         d_in = ctx->in_stage.as<uint8_t>();
@@ -1081,7 +1100,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         return !e ? 0 : strcmp(e, "warp") == 0 ? 1 : strcmp(e, "lanes") == 0 ? 2 : strcmp(e, "lanes_small") == 0 ? 3 : 0;
     }();
     const bool use_lanes = forced_kernel ? forced_kernel >= 2 : nseg >= (size_t)ctx->num_sms * 81;   // crossover measured at ~11 k segments
-    if (use_lanes) CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
+    if (use_lanes || pipe_inf) CU(ctx->inf_scratch.reserve(inflate_lanes_scratch_bytes(ctx->num_sms)));
     CU(ctx->inf_carry.reserve((nseg ? nseg : 1) * sizeof(uint32_t)));
 
     InflateParams I;
@@ -1101,14 +1120,52 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     I.carry_flag = d_carry_flag;
     I.continuation = (flags & ZSB_CONTINUATION) ? 1 : 0;
     ctx->last_inflate_valid = false;
-    timing_mark(ctx, 2, true);
+    size_t piped_to = 0;   // pipe_inf: output bytes [0, piped_to) are already on their way to the host
     // beyond ~3 segments per lane of the default kernel's residency the small-table instance (12 warps per SM) is faster
-    const bool small_tables = forced_kernel ? forced_kernel == 3 : nseg >= (size_t)ctx->num_sms * 7 * 32 * 3;
-    if (use_lanes && small_tables) CU(launch_inflate_lanes_small(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
-    else if (use_lanes) CU(launch_inflate_lanes(I, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
-    else CU(launch_inflate(I, ctx->num_sms, st));
-    timing_mark(ctx, 2, false);
-    ctx->launches++;
+    auto launch_one = [&](const InflateParams& J) -> int {
+        const bool lanes = forced_kernel ? forced_kernel >= 2 : J.nseg >= (uint32_t)ctx->num_sms * 81;
+        const bool small_tables = forced_kernel ? forced_kernel == 3 : J.nseg >= (uint32_t)ctx->num_sms * 7 * 32 * 3;
+        timing_mark(ctx, 2, true);
+        if (lanes && small_tables) CU(launch_inflate_lanes_small(J, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+        else if (lanes) CU(launch_inflate_lanes(J, ctx->num_sms, ctx->inf_scratch.as<uint8_t>(), ctx->inf_scratch.cap, st));
+        else CU(launch_inflate(J, ctx->num_sms, st));
+        timing_mark(ctx, 2, false);
+        ctx->launches++;
+        return ZSB_OK;
+    };
+    if (pipe_inf) {
+        CU(cudaMemsetAsync(d_carry_flag, 0, sizeof(unsigned int), st));
+        int b = 0;
+        for (size_t k0 = 0; k0 < nseg; k0 += pipe_per, b++) {
+            const size_t k1 = std::min(nseg, k0 + pipe_per);
+            InflateParams J = I;
+            J.seg_end = d_seg_end + k0;
+            J.first_offset = k0 ? seg_end_offsets[k0 - 1] : I.first_offset;
+            J.nseg = (uint32_t)(k1 - k0);
+            J.out = d_out + k0 * seg_size;
+            J.out_cap = total_out > k0 * seg_size ? total_out - k0 * seg_size : 0;
+            J.seg_out_len = I.seg_out_len + k0;
+            J.seg_status = I.seg_status + k0;
+            J.seg_carry = I.seg_carry + k0;
+            J.continuation = (k0 > 0 || I.continuation) ? 1 : 0;
+            CU(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
+            CU(cudaMemsetAsync(d_work, 0, 2 * sizeof(unsigned int), st));
+            int rc = launch_one(J);
+            if (rc != ZSB_OK) return rc;
+            CU(cudaEventRecord(ctx->ev_done[b], st));
+            if (k1 < nseg) {   // every segment but the stream's last holds seg_size bytes (a wrong one fails the call below)
+                const size_t upto = std::min(out_cap, k1 * seg_size);
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+                if (upto > piped_to) {
+                    CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + piped_to, d_out + piped_to, upto - piped_to, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    piped_to = upto;
+                }
+            }
+        }
+    } else {
+        int rc = launch_one(I);
+        if (rc != ZSB_OK) return rc;
+    }
     std::vector<int> status(nseg);
     std::vector<uint32_t> lens(nseg);
     uint32_t got_adler = 1;
@@ -1129,6 +1186,7 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
             char buf[160];
             snprintf(buf, sizeof buf, "%s (segment %zu)", kInflateMsg[e], k);
             // the reference reports only the message; the segment index is appended for the batch caller
+            if (pipe_inf) cudaStreamSynchronize(ctx->copy_stream);   // no copy into the caller's buffer outlives the call
             return fail(ctx, (e == IE_TRUNCATED || e == IE_OUTPUT_OVERFLOW) ? ZSB_BUF_ERROR : ZSB_DATA_ERROR, buf);
         }
         produced += lens[k];
@@ -1142,17 +1200,26 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         ctx->last_inflate_valid = true;
     }
     if (carry_flag) {   // Q14: Rle segments that open with a run of the previous segment's last byte
+        if (pipe_inf) {
+            CU(cudaStreamSynchronize(ctx->copy_stream));
+            piped_to = 0;   // the batches went out with placeholders: the completed output is copied once more below
+        }
         CU(launch_inflate_carry_fixup(I, st));
         ctx->launches++;
         // the first segment of the call has nothing before it here: its carried prefix is the caller's to fill (sharded streams)
         CU(cudaMemcpyAsync(&ctx->last_first_carry, ctx->inf_carry.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
+    if (pipe_inf && !carry_flag && produced > piped_to) {   // the last batch's bytes leave while the checksum pass runs
+        CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + piped_to, d_out + piped_to, produced - piped_to, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        piped_to = produced;
+    }
     // running Adler-32 of the output (InflateBlocks.cs:755,792) as a separate pass over the decoded bytes
     CU(launch_adler32(d_out, produced, 1u, ctx->seg_adler.as<uint2>(), (uint32_t)(achunks ? achunks : 1), d_adler, st));
     ctx->launches += 2;
     CU(cudaMemcpyAsync(&got_adler, d_adler, sizeof got_adler, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (pipe_inf) CU(cudaStreamSynchronize(ctx->copy_stream));
     if (adler) *adler = got_adler;
     if (has_trailer) {
         // segmented: the final block must be the empty static block `03 00` (Q12); then the big-endian Adler-32
@@ -1161,8 +1228,8 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
         const uint32_t want = ((uint32_t)tw[0] << 24) | ((uint32_t)tw[1] << 16) | ((uint32_t)tw[2] << 8) | tw[3];
         if (want != got_adler) return fail(ctx, ZSB_DATA_ERROR, "incorrect data check");  // Inflate.cs:335-342
     }
-    if (!(flags & ZSB_OUT_DEVICE) && produced) {
-        CU(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, st));
+    if (!(flags & ZSB_OUT_DEVICE) && produced > piped_to) {
+        CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + piped_to, d_out + piped_to, produced - piped_to, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return has_trailer ? ZSB_STREAM_END : ZSB_OK;

@@ -24,6 +24,23 @@ import torch
 import torch.distributed as dist
 
 
+_pinned = {}
+
+
+def _to_host(t: torch.Tensor):
+    """Small exchange tables go to the host through a reused pinned buffer: an asynchronous copy on the current stream and one
+    stream synchronisation instead of the pageable, device-wide `.cpu()`."""
+    if not t.is_cuda:
+        return t.tolist()
+    key = (t.shape, t.dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = _pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return buf.tolist()
+
+
 def shard_segments(nseg: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous, balanced [begin, end) range of segments of `rank`."""
     base, rem = divmod(nseg, world)
@@ -92,7 +109,7 @@ def deflate_sharded(engine, combine, local_in: torch.Tensor, seg_size: int, leve
     mine = torch.tensor([out_len, n, adler, 1 if gather_to is not None else 0], dtype=torch.int64, device=local_in.device)
     allv = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allv, mine, group=group)
-    table = torch.stack(allv).cpu().tolist()
+    table = _to_host(torch.stack(allv))
     gather_on = bool(table[0][3])
     res.sizes = [int(r[0]) for r in table]
     lengths = [int(r[1]) for r in table]
@@ -180,7 +197,7 @@ def inflate_sharded(engine, combine, local_comp: torch.Tensor, local_ends: torch
             mine[3] = local_out[out_len - 1]
         allv = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine, group=group)
-        table = torch.stack(allv).cpu().tolist()
+        table = _to_host(torch.stack(allv))
         res.lengths = [int(r[0]) for r in table]
         adlers = [int(r[1]) for r in table]
         carries = [int(r[2]) for r in table]

@@ -42,7 +42,7 @@ static struct {
     int base, loaded_end, cut0, cut1, forced;
     int blk_start;
 } M;
-static uint64_t st_search, st_overflow, st_over_nodes, st_pp;
+static uint64_t st_search, st_overflow, st_over_nodes, st_pp, st_ov_ins, st_ov_notuseful, st_ov_exact, st_ov_unknown;
 
 static inline int BY(int a) { return a < M.N ? M.seg[a] : M.seg[a - 32768]; }   /* stale bytes past the end */
 static int cp258(int a, int c)
@@ -80,7 +80,7 @@ static int resolve_at(const zso_deflater* s, int p, int la, int* mstart)
     if (p == M.forced) return 2;
     int cnt = 0, best = 2, sel = -1;
     const int nice = s->nice_match < la ? s->nice_match : la;
-    int c = -1, L = 0, j = 0, slow = 0;
+    int c = -1, L = 0, j = 0, slow = 0, ov_anchor = -1, ov_left = 0;
     st_search++;
     for (;;) {
         if (j < M.nk[p]) { c = p - M.dist[p][j]; L = M.len[p][j]; j++; }
@@ -88,9 +88,19 @@ static int resolve_at(const zso_deflater* s, int p, int la, int* mstart)
         else {   /* overflow: follow the all-position chain beyond the K-th node */
             if (!slow) { st_overflow++; slow = 1; }
             st_over_nodes++;
+            if (j != KMAX + 1) { ov_anchor = c; ov_left = K; }           /* first step: the anchor is the record's last node */
+            else if (ov_left == 0) { ov_anchor = c; ov_left = K; }       /* next round: the anchor is the previous round's last node */
             c = M.prev_all[c];
             if (c < 0 || p - c > MAXD) break;
+            ov_left--;
             L = cp258(p, c);
+            if (M.ins[c]) {   /* what kernel B could tell from the records alone: lcp(p,c) vs min(lcp(p,anchor), lcp(anchor,c)) */
+                int lpa = cp258(p, ov_anchor), lac = cp258(ov_anchor, c);
+                st_ov_ins++;
+                if ((lpa >= 3 && lac < 3) || (lpa < 3 && lac >= 3)) st_ov_notuseful++;
+                else if (lpa >= 3 && lac >= 3 && lpa != lac) st_ov_exact++;
+                else st_ov_unknown++;
+            }
             j = KMAX + 1;
         }
         if (!M.ins[c]) continue;
@@ -247,6 +257,9 @@ int main(int argc, char** argv)
     printf("%s seg=%zu L%d K=%d: ref %zu B, model %zu B: %s;  searches/pp %.3f overflow/search %.4f nodes/overflow %.1f\n", argv[1], seg,
            level, K, la, lb, same ? "IDENTICAL" : "DIFFERENT", (double)st_search / (double)(st_pp ? st_pp : 1),
            (double)st_overflow / (double)(st_search ? st_search : 1), (double)st_over_nodes / (double)(st_overflow ? st_overflow : 1));
+    printf("  overflow walks: inserted nodes %llu: not useful by the min rule %.3f, exact by the min rule %.3f, need bytes %.3f\n",
+           (unsigned long long)st_ov_ins, (double)st_ov_notuseful / (double)(st_ov_ins ? st_ov_ins : 1),
+           (double)st_ov_exact / (double)(st_ov_ins ? st_ov_ins : 1), (double)st_ov_unknown / (double)(st_ov_ins ? st_ov_ins : 1));
     return same ? 0 : 1;
 }
 #endif

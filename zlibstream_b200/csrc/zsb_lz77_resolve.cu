@@ -31,6 +31,9 @@ namespace zsb {
 namespace {
 
 constexpr int RB_WARPS = 8;
+#ifndef ZSB_RB_BLOCKS
+#define ZSB_RB_BLOCKS 4   // CTAs per SM: 32 warps at 64 registers (5 = 40 warps at 48 registers with spills measured slower)
+#endif
 constexpr int RING_WORDS = W_SIZE / 32;   // inserted bits of the last 32768 positions
 
 __device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* q)
@@ -133,7 +136,7 @@ __device__ __forceinline__ void slow_search(const uint4* rec, const uint8_t* seg
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(RB_WARPS * 32, 4) lz77_resolve_kernel(Lz77Params P)
+__global__ void __launch_bounds__(RB_WARPS * 32, ZSB_RB_BLOCKS) lz77_resolve_kernel(Lz77Params P)
 {
     __shared__ uint32_t ring_all[RB_WARPS][RING_WORDS];
     const int lane = threadIdx.x & 31;

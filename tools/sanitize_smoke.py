@@ -39,6 +39,37 @@ def main():
         ok = ok and dec == data
         print(f"{'ok  ' if ok else 'FAIL'} {name} seg={ss} L{level} S{strategy} hv={hv}", flush=True)
         bad += not ok
+    # round-2 paths: level 0, sync / partial flush (chained segments, shared edge bytes), one-piece streams, the PNG front end,
+    # the piped host-buffer inflate
+    for name, kw, mode in (("sync", dict(sync_flush=True), 2), ("partial", dict(partial_flush=True), 1)):
+        for level in (1, 6):
+            want, wends = orc.deflate_writes(text, seg, level, 0, 0, flush_mode=mode)
+            got, ends, _ = eng.deflate_segments(text, seg, level, 0, **kw)
+            dec, _ = eng.inflate_stream(got, len(text))
+            ok = got == want and ends == wends and dec == text
+            print(f"{'ok  ' if ok else 'FAIL'} {name} flush L{level}", flush=True)
+            bad += not ok
+    got, ends, _ = eng.deflate_segments(text, seg, 0, 0)
+    ok = got == orc.deflate_segments(text, seg, 0, 0)[0] and eng.inflate_segments(got, ends, seg, len(text))[0] == text
+    for level in (1, 6):
+        one, _ = eng.deflate_stream(text[:200001], level)
+        ok = ok and one == orc.deflate_oneshot(text[:200001], level)[0] and eng.inflate_stream(one, 200001)[0] == text[:200001]
+    print(f"{'ok  ' if ok else 'FAIL'} level 0, one-piece streams", flush=True)
+    bad += not ok
+    sys.path.insert(0, "oracle")
+    import numpy as np
+    import png_ref
+    px = np.random.RandomState(5).randint(0, 256, size=(60, 500, 4)).astype(np.uint8).tobytes()
+    png = eng.png_encode(px, 500, 60, 6, 5, level=6, strategy=1, idat_bytes=65536)
+    ok = png_ref.decode(png)["pixels"] == px
+    print(f"{'ok  ' if ok else 'FAIL'} png", flush=True)
+    bad += not ok
+    os.environ["ZSB_INFLATE_PIPE_SEGMENTS"] = "4"
+    want, wends, _ = orc.deflate_segments(runs + text, seg, 6, 3)
+    ok = eng.inflate_segments(want, wends, seg, len(runs + text))[0] == runs + text
+    os.environ.pop("ZSB_INFLATE_PIPE_SEGMENTS")
+    print(f"{'ok  ' if ok else 'FAIL'} piped host inflate (Rle carries)", flush=True)
+    bad += not ok
     assert eng.adler32(text) == zlib.adler32(text)
     eng.close()
     print("sanitize_smoke:", "all identical" if not bad else f"{bad} FAILED")

@@ -15,7 +15,7 @@ import synth  # noqa: E402
 from zlibstream_b200 import Engine  # noqa: E402
 
 NAMES = {16: "chunks", 17: "cyc_chunk_total", 18: "cyc_linker", 19: "cyc_linker_throttled", 20: "cyc_walkers_wait(sum)",
-         21: "cyc_walkers(sum)", 22: "cyc_stage_slide", 24: "groups", 25: "evals", 26: "steps", 27: "slow_searches", 28: "general_groups"}
+         21: "cyc_walkers(sum)", 22: "cyc_stage_slide", 23: "cyc_linker_waits_mail", 24: "groups", 25: "evals", 26: "steps", 27: "slow_searches", 28: "general_groups"}
 
 
 def main():

@@ -1,8 +1,12 @@
 // zsb_inflate_lanes.cu -- the lane-per-segment inflate kernel (state machine and table build: zsb_inflate_lanes.cuh).
 //
-// One warp per CTA, one segment per lane; each lane pulls its next segment from the work counter as soon as it is done,
-// so a warp never waits for its slowest lane beyond the iteration in flight.  Shared memory per CTA: 32 LaneTables
-// (45 KiB) + the build scratch (2 KiB) => 4 CTAs per SM.
+// One CTA per SM with as many warps as shared memory holds tables for, one segment per lane; each lane pulls its next
+// segment from the work counter as soon as it is done, so a warp never waits for its slowest lane beyond the iteration in
+// flight, and the warps of a CTA never wait for each other except for the build scratch.  Shared memory per CTA: 32
+// LaneTables per warp (29 KiB; 15.5 KiB in the small instance) + ONE build scratch (2 KiB): a build takes ~2 k cycles
+// and a warp asks for one every ~1 M cycles, so the warps take turns on it behind a lock.  (One warp per CTA with a
+// scratch each, the round-1 layout, pays 1 KiB of per-CTA reservation + 2 KiB of scratch per warp: 12 warps per SM for
+// the small instance instead of 14.)
 #include "zsb_inflate_lanes.cuh"
 
 #include <cstdlib>
@@ -20,7 +24,15 @@ using namespace ZSB_LN_NS;
 namespace {
 
 static_assert(sizeof(LaneTables) % 4 == 0 && sizeof(WarpScratch) % 8 == 0, "shared-memory layout: scratch first, then the tables");
-size_t lane_smem(int segs_per_warp) { return sizeof(WarpScratch) + (size_t)segs_per_warp * sizeof(LaneTables); }
+constexpr int MAX_WARPS = 16;   // per CTA (= per SM): 118 registers per thread allow no more
+// Warps per SM at 32 segments per warp.  The tables of the small instance would fit 14 times, but past 196 KiB of shared
+// memory the SM's L1 shrinks from 60 to 28 KiB and every lane slows down by a third (the compressed input is read 4 bytes at
+// a time and the match sources 8: both live on L1 hits).  16 GiB of 64 KiB segments on a B200: 8 warps 111 GB/s, 10 126,
+// 11 131, 12 143, 13 131, 14 134.
+#ifndef ZSB_LN_WARPS_FULL
+#define ZSB_LN_WARPS_FULL MAX_WARPS
+#endif
+size_t lane_smem(int warps, int segs_per_warp) { return sizeof(WarpScratch) + (size_t)warps * segs_per_warp * sizeof(LaneTables); }
 
 __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 {
@@ -34,13 +46,16 @@ __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 // segs_per_warp (S): lanes 0..S-1 decode a segment each, the others only help with the table builds.  Fewer segments
 // per warp = fewer divergent paths serialised per iteration and more warps for the same number of segments; the
 // launcher picks S from the number of segments so that the SMs have enough warps to hide latency.
-__global__ void __launch_bounds__(32) ZSB_LN_KERNEL(InflateParams P, uint8_t* scratch, int segs_per_warp)
+__global__ void __launch_bounds__(32 * MAX_WARPS) ZSB_LN_KERNEL(InflateParams P, uint8_t* scratch, int segs_per_warp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& sc = *reinterpret_cast<WarpScratch*>(smem);
-    LaneTables* tabs = reinterpret_cast<LaneTables*>(smem + sizeof(WarpScratch));
-    const int lane = threadIdx.x;
-    uint8_t* my_scratch = scratch + ((size_t)blockIdx.x * 32 + lane) * SCRATCH_STRIDE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    LaneTables* tabs = reinterpret_cast<LaneTables*>(smem + sizeof(WarpScratch)) + warp * segs_per_warp;
+    if (threadIdx.x == 0) sc.lock = 0;
+    __syncthreads();
+    uint8_t* my_scratch = scratch + (gwarp * 32 + lane) * SCRATCH_STRIDE;
     uint8_t* glens = my_scratch;
     uint16_t* glong = reinterpret_cast<uint16_t*>(my_scratch + LENS_STRIDE);
     LaneTables& T = tabs[lane < segs_per_warp ? lane : 0];
@@ -57,6 +72,12 @@ __global__ void __launch_bounds__(32) ZSB_LN_KERNEL(InflateParams P, uint8_t* sc
         }
         // serve the lanes that wait for a table, one after the other, with the whole warp
         unsigned need = __ballot_sync(0xffffffffu, L.st == S_BUILD_BL || L.st == S_BUILD_LD);
+        const bool locked = need != 0 && blockDim.x > 32;
+        if (locked) {   // the scratch is the CTA's: every word of it is written by the build before the build reads it
+            if (lane == 0)
+                while (atomicCAS(&sc.lock, 0, 1) != 0) __nanosleep(200);
+            __syncwarp();
+        }
         while (need) {
             const int t = __ffs(need) - 1;
             need &= need - 1;
@@ -64,7 +85,7 @@ __global__ void __launch_bounds__(32) ZSB_LN_KERNEL(InflateParams P, uint8_t* sc
             const uint64_t bl = __shfl_sync(0xffffffffu, (unsigned long long)L.bl_lens, t);
             const int nl = __shfl_sync(0xffffffffu, L.nl, t), nd = __shfl_sync(0xffffffffu, L.nd, t);
             const int fixed = __shfl_sync(0xffffffffu, L.fixed, t);
-            uint8_t* t_scratch = scratch + ((size_t)blockIdx.x * 32 + t) * SCRATCH_STRIDE;
+            uint8_t* t_scratch = scratch + (gwarp * 32 + t) * SCRATCH_STRIDE;
             LaneTables& TT = tabs[t];
             HelperRegs R;
             __syncwarp();   // the target's code lengths (global) and everybody's table reads are done
@@ -79,6 +100,11 @@ __global__ void __launch_bounds__(32) ZSB_LN_KERNEL(InflateParams P, uint8_t* sc
             const int rc_l = sc.rc_l, rc_d = sc.rc_d;
             if (lane == t) after_build(L, ld, rc_l, rc_d);
             __syncwarp();
+        }
+        if (locked) {
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicExch(&sc.lock, 0);
         }
         if (__all_sync(0xffffffffu, L.st == S_EXIT)) break;
     }
@@ -156,11 +182,23 @@ size_t inflate_lanes_scratch_bytes(int num_sms)
 cudaError_t ZSB_LN_LAUNCH(const InflateParams& P, int num_sms, uint8_t* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
     if (P.nseg == 0) return cudaSuccess;
+    int smem_max = 0, dev = 0;
     {   // a per-device attribute: set on every launch (a process may drive several GPUs, one zsb_ctx each)
-        cudaError_t e = cudaFuncSetAttribute(ZSB_LN_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem(32));
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ZSB_LN_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
         if (e != cudaSuccess) return e;
     }
-    // Segments per warp: as many as still leave ~kWarpsWanted warps per SM (ZSB_INFLATE_SEGS_PER_WARP overrides).
+    // warps one SM holds with S segments per warp: shared memory for the tables, MAX_WARPS for the registers
+    auto warps_per_sm = [&](int S) {
+        int w = (int)(((size_t)smem_max - sizeof(WarpScratch)) / ((size_t)S * sizeof(LaneTables)));
+        const char* e = getenv("ZSB_INFLATE_WARPS");   // experiments: cap the warps per SM
+        const int cap = e ? atoi(e) : 0;
+        if (cap >= 1 && w > cap) w = cap;
+        else if (!cap && S == 32 && w > ZSB_LN_WARPS_FULL) w = ZSB_LN_WARPS_FULL;
+        return w > MAX_WARPS ? MAX_WARPS : w < 1 ? 1 : w;
+    };
+    // Segments per warp: as many as still leave enough warps per SM (ZSB_INFLATE_SEGS_PER_WARP overrides).
     const int forced = [] {
         const char* e = getenv("ZSB_INFLATE_SEGS_PER_WARP");
         const int v = e ? atoi(e) : 0;
@@ -171,17 +209,17 @@ cudaError_t ZSB_LN_LAUNCH(const InflateParams& P, int num_sms, uint8_t* scratch,
         // measured on B200 (profiles/r01i_inflate_sweep.txt, r01n_inflate_sweep.txt): with enough segments to keep every SM's resident
         // warps full, 32 per warp is fastest (issue slots are shared 32 ways); below that, 16 per warp trades issue
         // efficiency for more warps in flight (16384 segments: 58.5 GB/s at 16, 55.9 at 32, 33.9 at 6)
-        int full = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, ZSB_LN_KERNEL, 32, lane_smem(32)) != cudaSuccess || full < 1) full = 1;
-        S = (size_t)P.nseg * 4 >= (size_t)num_sms * full * 32 * 3 ? 32 : 16;
+        S = (size_t)P.nseg * 4 >= (size_t)num_sms * warps_per_sm(32) * 32 * 3 ? 32 : 16;
     }
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ZSB_LN_KERNEL, 32, lane_smem(S)) != cudaSuccess || per_sm < 1) per_sm = 1;
-    int ctas = num_sms * per_sm;
-    const int need = (int)((P.nseg + S - 1) / S);
-    if (ctas > need) ctas = need;
-    if ((size_t)ctas * 32 * SCRATCH_STRIDE > scratch_bytes) return cudaErrorInvalidValue;
-    ZSB_LN_KERNEL<<<ctas, 32, lane_smem(S), stream>>>(P, scratch, S);
+    int W = warps_per_sm(S);
+    const size_t need = ((size_t)P.nseg + S - 1) / S;            // warps that have a first segment to take
+    int ctas = num_sms;
+    if (need < (size_t)num_sms * W) {
+        W = (int)((need + num_sms - 1) / num_sms);
+        ctas = (int)((need + W - 1) / W);
+    }
+    if ((size_t)ctas * W * 32 * SCRATCH_STRIDE > scratch_bytes) return cudaErrorInvalidValue;
+    ZSB_LN_KERNEL<<<ctas, 32 * W, lane_smem(W, S), stream>>>(P, scratch, S);
     return cudaGetLastError();
 }
 

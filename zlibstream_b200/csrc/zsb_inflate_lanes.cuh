@@ -67,13 +67,14 @@ struct LaneTables {                       // per lane, shared memory
     uint8_t long_d[32];
 };
 
-struct WarpScratch {                      // per warp, shared memory: the cooperative table build
+struct WarpScratch {                      // per CTA, shared memory: the cooperative table build (one warp at a time, see `lock`)
     unsigned long long loc[32];           // per helper: count of each literal/length code length, 4 bits each
     uint16_t pre[16][32];                 // [length][helper]: symbols of that length owned by earlier helpers
     uint8_t pre_d[16][32];
     uint8_t dlen[32];                     // code length of the small alphabet's symbol `helper`
     uint16_t cnt_l[16], cnt_d[16], first_l[16], first_d[16], off_l[16], off_d[16];
     int rc_l, rc_d;
+    int lock, pad_;                       // 1 while a warp of the CTA runs a build
 };
 
 struct HelperRegs {                       // what a helper lane carries from phase 0 to phase 3

@@ -15,7 +15,7 @@
 // coordinates, rebased at a slide like SlideHash), and a ring of 34816 distances "position -> its predecessor" -- 2048
 // more slots than the 32506 a chain may reach back, which is what lets 32 warps walk chains while later positions are
 // being linked.  Linking is the one ordered step: groups of 32 consecutive positions take turns (a counter in shared
-// memory); inside a group, equal hashes are found with 15 ballots.  Adler-32 partial sums are taken from the staged
+// memory); inside a group, equal hashes are found with one warp match.  Adler-32 partial sums are taken from the staged
 // bytes (no extra pass over the input).
 //
 // Record (32 bytes per position, HBM): 10 x u16 distance, 10 x u8 (prefix - 3), then 16 bits: ten flags "prefix >= 3",
@@ -162,13 +162,8 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                 uint32_t scan[4];
                 lds16(win, idx, scan);
                 const uint32_t h = hash4(crc, __funnelshift_r(scan[0], scan[1], 16), P.hash_variant);   // Q1: bytes +2..+5
-                // lanes of this group with my hash: 15 ballots
-                uint32_t same = 0xffffffffu;
-#pragma unroll
-                for (int b = 0; b < 15; b++) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, (h >> b) & 1u);
-                    same &= ((h >> b) & 1u) ? bal : ~bal;
-                }
+                // lanes of this group with my hash (one MATCH instruction; 15 ballots cost ~100)
+                const uint32_t same = __match_any_sync(0xffffffffu, h);
                 const uint32_t below = same & lt;
                 const bool leader = below == 0, tail = (same >> lane) == 1u;
                 const int src = leader ? lane : 31 - __clz(below);
@@ -210,11 +205,14 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                             uint32_t cw[4];
                             lds16(win, cidx, cw);
                             const uint32_t x0 = cw[0] ^ scan[0], x1 = cw[1] ^ scan[1], x2 = cw[2] ^ scan[2], x3 = cw[3] ^ scan[3];
-                            int len;
-                            if (x0) len = (__ffs(x0) - 1) >> 3;
-                            else if (x1) len = 4 + ((__ffs(x1) - 1) >> 3);
-                            else if (x2) len = 8 + ((__ffs(x2) - 1) >> 3);
-                            else if (x3) len = 12 + ((__ffs(x3) - 1) >> 3);
+                            // first differing word without branches: the lanes of a warp stop in different words
+                            uint32_t m = x2 ? x2 : x3;
+                            int len = x2 ? 8 : 12;
+                            m = x1 ? x1 : m;
+                            len = x1 ? 4 : len;
+                            m = x0 ? x0 : m;
+                            len = x0 ? 0 : len;
+                            if (m) len += (__ffs(m) - 1) >> 3;
                             else len = prefix_from(win, idx, cidx, 16);
                             useful = 1;
                             L = (uint32_t)(len - MIN_MATCH);

@@ -31,7 +31,7 @@ constexpr int LA_THREADS = 1024;
 constexpr int WIN_AHEAD = 1024;                       // bytes staged beyond the chunk being linked (>= 258 + 16 + 5)
 constexpr int WIN_BYTES = WINDOW_SIZE + WIN_AHEAD;    // 66560
 constexpr int WIN_PADDED = WIN_BYTES + 64;
-constexpr int RING = W_SIZE + 2048;                   // slots of the distance ring: MAX_DIST + the run-ahead of the linking
+constexpr int RING = W_SIZE + 2048;                   // slots of the distance ring: MAX_DIST + twice the run-ahead of the linking
 
 __device__ __forceinline__ uint32_t hash4(const uint16_t* crc, uint32_t v, int hash_variant)
 {
@@ -155,36 +155,44 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
             }
 
             // ---- link and walk: groups of 32 positions, warp w takes groups w, w + 32, ... of this 32 KiB chunk ----
+            // (A warp's walk of one group is ~800 dependent instructions = ~11 k cycles, and 32 warps walk at once: ~350 cycles
+            // per group, which is what the kernel takes.  The ordered step is not the bound: two or four groups per turn
+            // change nothing, measured.)
             for (int t = 0; t < W_SIZE / LA_THREADS; t++) {
                 const int g = t * 32 + warp;
                 const int idx = W_SIZE + g * 32 + lane;          // window index
                 const int a = W_SIZE * c + g * 32 + lane;        // position in the segment
-                uint32_t scan[4];
-                lds16(win, idx, scan);
-                const uint32_t h = hash4(crc, __funnelshift_r(scan[0], scan[1], 16), P.hash_variant);   // Q1: bytes +2..+5
-                // lanes of this group with my hash (one MATCH instruction; 15 ballots cost ~100)
-                const uint32_t same = __match_any_sync(0xffffffffu, h);
-                const uint32_t below = same & lt;
-                const bool leader = below == 0, tail = (same >> lane) == 1u;
-                const int src = leader ? lane : 31 - __clz(below);
-                // -- ordered: InsertString of every position, in position order --
-                if (lane == 0) {   // far from the turn: sleep (31 spinning warps would take the issue slots of the one that links)
-                    int tnow;
-                    while ((tnow = *turn) != g)
-                        if (g - tnow > 2) __nanosleep(g - tnow > 8 ? 800 : 100);   // measured flat around these values
+                uint32_t d;
+                {
+                    uint32_t scan[4];
+                    lds16(win, idx, scan);
+                    const uint32_t h = hash4(crc, __funnelshift_r(scan[0], scan[1], 16), P.hash_variant);   // Q1: bytes +2..+5
+                    // lanes of this group with my hash (one MATCH instruction; 15 ballots cost ~100)
+                    const uint32_t same = __match_any_sync(0xffffffffu, h);
+                    const uint32_t below = same & lt;
+                    const bool leader = below == 0, tail = (same >> lane) == 1u;
+                    const int src = leader ? lane : 31 - __clz(below);
+                    // -- ordered: InsertString of every position, in position order --
+                    if (lane == 0) {   // far from the turn: sleep (31 spinning warps would take the issue slots of the one that links)
+                        int tnow;
+                        while ((tnow = *turn) != g)
+                            if (g - tnow > 2) __nanosleep(g - tnow > 8 ? 800 : 100);   // measured flat around these values
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    uint32_t pred = leader ? (uint32_t)head[h] : 0u;
+                    const uint32_t pidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
+                    if (!leader) pred = pidx;
+                    if (tail) head[h] = (uint16_t)idx;
+                    d = pred ? (uint32_t)idx - pred : 0u;
+                    if (d > (uint32_t)MAX_DIST) d = 0;
+                    ring[(uint32_t)a % RING] = (uint16_t)d;
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) *turn = g + 1;
                 }
-                __syncwarp();
-                __threadfence_block();
-                uint32_t pred = leader ? (uint32_t)head[h] : 0u;
-                const uint32_t pidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
-                if (!leader) pred = pidx;
-                if (tail) head[h] = (uint16_t)idx;
-                uint32_t d = pred ? (uint32_t)idx - pred : 0u;
-                if (d > (uint32_t)MAX_DIST) d = 0;
-                ring[(uint32_t)a % RING] = (uint16_t)d;
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) *turn = g + 1;
+                uint32_t scan[4];
+                lds16(win, idx, scan);   // again: cheaper than keeping four registers across the ordered step (measured)
                 // -- the LK nearest predecessors and their common prefix lengths --
                 uint32_t dd[LZ_LIST_K], ll[LZ_LIST_K];
                 uint32_t usem = 0, edge = 0;
@@ -200,6 +208,8 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                     if (inwin && (k == 0 || total + (int)d < MAX_DIST)) {
                         total += (int)d;
                         const int cidx = idx - total;
+                        // the next link first: the walk is a chain of dependent shared-memory reads, the compare is not on it
+                        const uint32_t d_next = ring[(uint32_t)(a - total) % RING];
                         uint32_t useful = 0, L = 0;
                         if (((lds_u32_unaligned(win, cidx) ^ scan[0]) & 0x00ffffffu) == 0) {
                             uint32_t cw[4];
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                         usem |= useful << k;
                         ll[k] = L;
                         nk = k + 1;
-                        d = ring[(uint32_t)(a - total) % RING];
+                        d = d_next;
                     } else d = 0;
                 }
                 const uint32_t more = (d != 0 && total + (int)d <= MAX_DIST) ? 1u : edge;

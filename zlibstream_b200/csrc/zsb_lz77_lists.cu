@@ -31,6 +31,7 @@ constexpr int LA_THREADS = 1024;
 constexpr int WIN_AHEAD = 1024;                       // bytes staged beyond the chunk being linked (>= 258 + 16 + 5)
 constexpr int WIN_BYTES = WINDOW_SIZE + WIN_AHEAD;    // 66560
 constexpr int WIN_PADDED = WIN_BYTES + 64;
+constexpr int LA_NEAR = 12;                           // turns away at which a warp enters its barrier (< 15 - 1)
 constexpr int RING = W_SIZE + 2048;                   // slots of the distance ring: MAX_DIST + twice the run-ahead of the linking
 
 __device__ __forceinline__ uint32_t hash4(const uint16_t* crc, uint32_t v, int hash_variant)
@@ -155,9 +156,6 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
             }
 
             // ---- link and walk: groups of 32 positions, warp w takes groups w, w + 32, ... of this 32 KiB chunk ----
-            // (A warp's walk of one group is ~800 dependent instructions = ~11 k cycles, and 32 warps walk at once: ~350 cycles
-            // per group, which is what the kernel takes.  The ordered step is not the bound: two or four groups per turn
-            // change nothing, measured.)
             for (int t = 0; t < W_SIZE / LA_THREADS; t++) {
                 const int g = t * 32 + warp;
                 const int idx = W_SIZE + g * 32 + lane;          // window index
@@ -172,23 +170,31 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                     const uint32_t below = same & lt;
                     const bool leader = below == 0, tail = (same >> lane) == 1u;
                     const int src = leader ? lane : 31 - __clz(below);
+                    uint32_t slot = (uint32_t)a % RING;
+                    int bar_in = 1 + g % 15, bar_out = 1 + (g + 1) % 15;
+                    asm volatile("" : "+r"(slot), "+r"(bar_in), "+r"(bar_out));   // computed here, not inside the ordered step
                     // -- ordered: InsertString of every position, in position order --
-                    if (lane == 0) {   // far from the turn: sleep (31 spinning warps would take the issue slots of the one that links)
-                        int tnow;
-                        while ((tnow = *turn) != g)
-                            if (g - tnow > 2) __nanosleep(g - tnow > 8 ? 800 : 100);   // measured flat around these values
+                    // The turn passes through a hardware barrier (no polling, ~50 % of the issue slots went there): the holder
+                    // of turn g - 1 arrives at barrier 1 + g % 15, the holder of turn g waits on it.  Fifteen barriers serve the
+                    // turns that are at most NEAR away; a warp further ahead than that sleeps on the counter first, so a barrier
+                    // is never entered for turn g + 15 before turn g is through.  The barrier orders the shared-memory accesses
+                    // of the two warps (PTX: barrier.sync / barrier.arrive), turn after turn.
+                    if (g > 0) {
+                        if (lane == 0) {
+                            int tnow;
+                            while (g - (tnow = *turn) > LA_NEAR) __nanosleep(g - tnow > 2 * LA_NEAR ? 800 : 200);
+                        }
+                        __syncwarp();
+                        asm volatile("barrier.sync %0, 64;" ::"r"(bar_in) : "memory");
                     }
-                    __syncwarp();
-                    __threadfence_block();
                     uint32_t pred = leader ? (uint32_t)head[h] : 0u;
                     const uint32_t pidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
                     if (!leader) pred = pidx;
                     if (tail) head[h] = (uint16_t)idx;
                     d = pred ? (uint32_t)idx - pred : 0u;
                     if (d > (uint32_t)MAX_DIST) d = 0;
-                    ring[(uint32_t)a % RING] = (uint16_t)d;
-                    __threadfence_block();
-                    __syncwarp();
+                    ring[slot] = (uint16_t)d;
+                    if (g + 1 < W_SIZE / 32) asm volatile("barrier.arrive %0, 64;" ::"r"(bar_out) : "memory");
                     if (lane == 0) *turn = g + 1;
                 }
                 uint32_t scan[4];

@@ -31,6 +31,7 @@ constexpr int LA_THREADS = 1024;
 constexpr int WIN_AHEAD = 1024;                       // bytes staged beyond the chunk being linked (>= 258 + 16 + 5)
 constexpr int WIN_BYTES = WINDOW_SIZE + WIN_AHEAD;    // 66560
 constexpr int WIN_PADDED = WIN_BYTES + 64;
+constexpr int NO_LINK = 0xFFFF;                       // ring entry of a position without a predecessor in reach (> MAX_DIST)
 constexpr int LA_NEAR = 12;                           // turns away at which a warp enters its barrier (< 15 - 1)
 constexpr int RING = W_SIZE + 2048;                   // slots of the distance ring: MAX_DIST + twice the run-ahead of the linking
 
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                 const int idx = W_SIZE + g * 32 + lane;          // window index
                 const int a = W_SIZE * c + g * 32 + lane;        // position in the segment
                 uint32_t d;
+                int rs;   // ring slot of the node the walk stands on
                 {
                     uint32_t scan[4];
                     lds16(win, idx, scan);
@@ -191,9 +193,10 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                     const uint32_t pidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
                     if (!leader) pred = pidx;
                     if (tail) head[h] = (uint16_t)idx;
-                    d = pred ? (uint32_t)idx - pred : 0u;
-                    if (d > (uint32_t)MAX_DIST) d = 0;
+                    d = pred ? (uint32_t)idx - pred : (uint32_t)NO_LINK;
+                    if (d > (uint32_t)MAX_DIST) d = NO_LINK;   // no predecessor, or one out of reach: the chain ends here
                     ring[slot] = (uint16_t)d;
+                    rs = (int)slot;
                     if (g + 1 < W_SIZE / 32) asm volatile("barrier.arrive %0, 64;" ::"r"(bar_out) : "memory");
                     if (lane == 0) *turn = g + 1;
                 }
@@ -209,13 +212,15 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                     ll[k] = 0;
                     // a node at exactly MAX_DIST can only be visited first (Deflate.cs:1031,1096): listed as candidate 0 only,
                     // otherwise left to kernel B's chain walk ("the chain goes on")
-                    const bool inwin = d != 0 && total + (int)d <= MAX_DIST;
-                    if (inwin && k > 0 && total + (int)d == MAX_DIST) edge = 1u;
-                    if (inwin && (k == 0 || total + (int)d < MAX_DIST)) {
+                    const int nt = total + (int)d;   // NO_LINK takes it past every limit, and stays there
+                    if (k > 0 && nt == MAX_DIST) edge = 1u;
+                    if (nt < MAX_DIST + (k == 0 ? 1 : 0)) {
                         total += (int)d;
                         const int cidx = idx - total;
                         // the next link first: the walk is a chain of dependent shared-memory reads, the compare is not on it
-                        const uint32_t d_next = ring[(uint32_t)(a - total) % RING];
+                        rs -= (int)d;
+                        rs += rs < 0 ? RING : 0;
+                        const uint32_t d_next = ring[rs];
                         uint32_t useful = 0, L = 0;
                         if (((lds_u32_unaligned(win, cidx) ^ scan[0]) & 0x00ffffffu) == 0) {
                             uint32_t cw[4];
@@ -238,9 +243,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                         ll[k] = L;
                         nk = k + 1;
                         d = d_next;
-                    } else d = 0;
+                    } else d = NO_LINK;
                 }
-                const uint32_t more = (d != 0 && total + (int)d <= MAX_DIST) ? 1u : edge;
+                const uint32_t more = total + (int)d <= MAX_DIST ? 1u : edge;
                 uint4 r0, r1;
                 r0.x = dd[0] | (dd[1] << 16);
                 r0.y = dd[2] | (dd[3] << 16);

@@ -26,6 +26,10 @@
 // one shuffle per match.  Everything else runs the general loop, which spells every rule out per parse point.
 #include "zsb_kernels.cuh"
 
+#ifndef ZSB_RB_PREFETCH
+#define ZSB_RB_PREFETCH "prefetch.global.L2"
+#endif
+
 namespace zsb {
 
 namespace {
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, ZSB_RB_BLOCKS) lz77_resolve_ker
                         // the walk will need the record of the last listed node if the parse lands here: ask for it now
                         if (r_over && nk > 0) {
                             const uint4* nr = rec + (size_t)(a - (int)dist_at(r0, r1.x, nk - 1)) * 2;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nr));
+                            asm volatile(ZSB_RB_PREFETCH " [%0];" ::"l"(nr));
                         }
                     }
                     uint32_t OVm = __ballot_sync(0xffffffffu, r_over);

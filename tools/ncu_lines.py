@@ -1,7 +1,7 @@
 """Per-source-line view of an ncu capture (development tool): joins the SASS page of an .ncu-rep (instructions executed,
 stall samples per instruction) with nvdisasm's line table of the same build of libzsb200.so.
 
-  python tools/ncu_lines.py gpurun_out/prof.ncu-rep lz77_resolve [top]      # kernel-name regex
+  python tools/ncu_lines.py gpurun_out/prof.ncu-rep lz77_resolve [top [mangled-name regex]]      # kernel-name regex
 """
 import csv
 import os
@@ -44,13 +44,14 @@ def line_table(kernel_re):
 def main():
     rep, kre = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    mre = sys.argv[4] if len(sys.argv) > 4 else kre     # regex on the MANGLED name (template instances: ...ILb0E...)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
     hdr = rows[hi]
     ia, ie, ism, ith = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
     stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-    table = line_table(kre)
+    table = line_table(mre)
     base = None
     agg = {}
     srcs = {}

@@ -14,9 +14,10 @@
 // slides by 32 KiB like the reference's (bulk async copy refills), head[32768] (latest position of every hash, window
 // coordinates, rebased at a slide like SlideHash), and a ring of 34816 distances "position -> its predecessor" -- 2048
 // more slots than the 32506 a chain may reach back, which is what lets 32 warps walk chains while later positions are
-// being linked.  Linking is the one ordered step: groups of 32 consecutive positions take turns (a counter in shared
-// memory); inside a group, equal hashes are found with one warp match.  Adler-32 partial sums are taken from the staged
-// bytes (no extra pass over the input).
+// being linked.  Linking is the one ordered step: groups of 32 consecutive positions take turns, and the turn passes from
+// warp to warp through named hardware barriers (a polled shared-memory flag cost half of the SM's issue slots); inside a
+// group, equal hashes are found with one warp match.  Adler-32 partial sums are taken from the staged bytes (no extra
+// pass over the input).
 //
 // Record (32 bytes per position, HBM): 10 x u16 distance, 10 x u8 (prefix - 3), then 16 bits: ten flags "prefix >= 3",
 // "the chain goes on", the number of candidates.

@@ -33,7 +33,10 @@ constexpr int WIN_AHEAD = 1024;                       // bytes staged beyond the
 constexpr int WIN_BYTES = WINDOW_SIZE + WIN_AHEAD;    // 66560
 constexpr int WIN_PADDED = WIN_BYTES + 64;
 constexpr int NO_LINK = 0xFFFF;                       // ring entry of a position without a predecessor in reach (> MAX_DIST)
-constexpr int LA_NEAR = 12;                           // turns away at which a warp enters its barrier (< 15 - 1)
+#ifndef ZSB_LA_NEAR
+#define ZSB_LA_NEAR 12
+#endif
+constexpr int LA_NEAR = ZSB_LA_NEAR;                           // turns away at which a warp enters its barrier (< 15 - 1)
 constexpr int RING = W_SIZE + 2048;                   // slots of the distance ring: MAX_DIST + twice the run-ahead of the linking
 
 __device__ __forceinline__ uint32_t hash4(const uint16_t* crc, uint32_t v, int hash_variant)
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                     const int src = leader ? lane : 31 - __clz(below);
                     uint32_t slot = (uint32_t)a % RING;
                     int bar_in = 1 + g % 15, bar_out = 1 + (g + 1) % 15;
-                    asm volatile("" : "+r"(slot), "+r"(bar_in), "+r"(bar_out));   // computed here, not inside the ordered step
+                    uint32_t pidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);   // predecessor inside the group (non-leaders)
+                    asm volatile("" : "+r"(slot), "+r"(bar_in), "+r"(bar_out), "+r"(pidx));   // computed here, not inside the ordered step
                     // -- ordered: InsertString of every position, in position order --
                     // The turn passes through a hardware barrier (no polling, ~50 % of the issue slots went there): the holder
                     // of turn g - 1 arrives at barrier 1 + g % 15, the holder of turn g waits on it.  Fifteen barriers serve the
@@ -190,9 +194,7 @@ __global__ void __launch_bounds__(LA_THREADS, 1) lz77_lists_kernel(Lz77Params P)
                         __syncwarp();
                         asm volatile("barrier.sync %0, 64;" ::"r"(bar_in) : "memory");
                     }
-                    uint32_t pred = leader ? (uint32_t)head[h] : 0u;
-                    const uint32_t pidx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
-                    if (!leader) pred = pidx;
+                    const uint32_t pred = leader ? (uint32_t)head[h] : pidx;
                     if (tail) head[h] = (uint16_t)idx;
                     d = pred ? (uint32_t)idx - pred : (uint32_t)NO_LINK;
                     if (d > (uint32_t)MAX_DIST) d = NO_LINK;   // no predecessor, or one out of reach: the chain ends here

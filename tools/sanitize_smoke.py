@@ -23,6 +23,9 @@ def main():
     cases = [("text", text, seg, 1, 0), ("text", text, seg, 3, 0), ("text", text, seg, 6, 0), ("text", text[:2 * seg + 99], seg, 9, 0),
              ("mixed", mixed, 262144, 1, 0), ("mixed", mixed, 262144, 6, 0), ("png", png, seg, 6, 1), ("png", png, seg, 6, 2),
              ("png", png, seg, 6, 3), ("runs", runs, seg, 6, 3), ("runs", runs, seg, 1, 4), ("text", text, seg, 1, 0, 1)]
+    only = os.environ.get("ZSB_SMOKE_ONLY", "")   # "l1": the level-1 kernels and the inflate kernels only (a short racecheck)
+    if only == "l1":
+        cases = [c for c in cases if c[3] == 1]
     bad = 0
     for case in cases:
         name, data, ss, level, strategy = case[:5]
@@ -39,6 +42,10 @@ def main():
         ok = ok and dec == data
         print(f"{'ok  ' if ok else 'FAIL'} {name} seg={ss} L{level} S{strategy} hv={hv}", flush=True)
         bad += not ok
+    if only:
+        eng.close()
+        print("sanitize_smoke:", "all identical" if not bad else f"{bad} FAILED")
+        sys.exit(1 if bad else 0)
     # round-2 paths: level 0, sync / partial flush (chained segments, shared edge bytes), one-piece streams, the PNG front end,
     # the piped host-buffer inflate
     for name, kw, mode in (("sync", dict(sync_flush=True), 2), ("partial", dict(partial_flush=True), 1)):

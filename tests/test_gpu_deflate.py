@@ -400,3 +400,18 @@ def test_multiwave_parity_with_the_oracle(engine, oracle, name, kind, ss, nseg, 
         finally:
             del os.environ["ZSB_INFLATE_KERNEL"]
         assert dad == want_adler and dec == data, (name, kernel)
+
+
+@pytest.mark.parametrize("kernel", ["lanes", "lanes_small"])
+@pytest.mark.parametrize("per_warp", [1, 3])
+def test_lane_inflate_with_several_warps_per_cta(engine, oracle, monkeypatch, kernel, per_warp):
+    """The lane kernels run one CTA per SM whose warps share ONE table-build scratch behind a lock
+    (zsb_inflate_lanes.cu).  With few segments per warp, 460 segments need more warps than there are SMs, so every CTA
+    holds several warps that build their tables at the same time (dynamic Huffman blocks: a build per block and lane)."""
+    ss, nseg = 65536, 460
+    data = _multiwave_input("text", ss * nseg + 77)
+    want, want_ends, want_adler = oracle.deflate_segments_parallel(data, ss, 6, 0)
+    monkeypatch.setenv("ZSB_INFLATE_KERNEL", kernel)
+    monkeypatch.setenv("ZSB_INFLATE_SEGS_PER_WARP", str(per_warp))
+    dec, dad = engine.inflate_segments(want, want_ends, ss, len(data))
+    assert dad == want_adler and dec == data

@@ -71,7 +71,7 @@ struct zsb_ctx {
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // host <-> device copies of one batch overlap the kernels of its neighbours
-    static constexpr int kMaxPipe = 8;
+    static constexpr int kMaxPipe = 16;          // pieces of a piped host-buffer call (events, totals)
     cudaEvent_t ev_in[kMaxPipe] = {}, ev_done[kMaxPipe] = {};
     uint64_t* h_totals = nullptr;           // pinned: output offset after each batch
     cudaStream_t stream = nullptr;
@@ -751,9 +751,12 @@ int zsb_deflate_segments(zsb_ctx* ctx, const void* in, size_t n, size_t seg_size
         // about four batches.  Level 1: the resolve kernel parses one segment per warp, 32 warps per SM, so a batch is a whole
         // number of those waves (4096 segments on 4736 warp slots cost a full wave each: 45 -> 56 ms per GiB); what is left over
         // goes FIRST, so that the kernels start after the shortest upload.  Other levels: a multiple of the SM count.
-        const size_t unit = use_lists ? (size_t)ctx->num_sms * 32 : (size_t)ctx->num_sms;
-        const size_t nb_target = env_size("ZSB_PIPE_BATCHES", 4);
-        size_t k = (nseg / unit + nb_target - 1) / nb_target;
+        // When the scratch holds the whole call (split schedule below: kernel A per piece, ONE resolve over everything), only
+        // kernel A runs per piece and it hands out one segment per SM: eight pieces, so that it starts after an eighth of the upload.
+        const bool whole_call = use_lists && batch >= nseg;
+        const size_t unit = (use_lists && !whole_call) ? (size_t)ctx->num_sms * 32 : (size_t)ctx->num_sms;
+        const size_t nb_target = env_size("ZSB_PIPE_BATCHES", whole_call ? (size_t)zsb_ctx::kMaxPipe : 4);
+        size_t k = ((nseg + unit - 1) / unit + nb_target - 1) / nb_target;   // => at most nb_target pieces
         if (k < 1) k = 1;
         size_t pb = k * unit;
         if (pb < batch) {
@@ -1021,8 +1024,9 @@ int zsb_inflate_segments(zsb_ctx* ctx, const void* in, size_t n, const uint64_t*
     const size_t pipe_min = env_size("ZSB_INFLATE_PIPE_SEGMENTS", 65536);   // tests lower it
     const bool pipe_inf = !(flags & (ZSB_IN_DEVICE | ZSB_OUT_DEVICE | ZSB_OFFSETS_DEVICE)) && !single && seg_end_offsets && nseg >= pipe_min && nseg >= 2;
     size_t pipe_per = 0;
+    constexpr size_t kInflatePieces = 8;
     if (pipe_inf) {
-        pipe_per = std::max<size_t>(std::max<size_t>(1, pipe_min / 4), (nseg + zsb_ctx::kMaxPipe - 1) / zsb_ctx::kMaxPipe);
+        pipe_per = std::max<size_t>(std::max<size_t>(1, pipe_min / 4), (nseg + kInflatePieces - 1) / kInflatePieces);
         CU(ctx->in_stage.reserve(n ? n : 1));
         d_in = ctx->in_stage.as<uint8_t>();
         if (n >= 2) memcpy(hdr, in, 2);

@@ -6,8 +6,12 @@
 #define ZSB_LN_NS lanes_small
 #define ZSB_LN_ROOT_L 7
 #define ZSB_LN_ROOT_D 5
+#ifndef ZSB_LN_LONG_L
 #define ZSB_LN_LONG_L 32
+#endif
+#ifndef ZSB_LN_WARPS_FULL
 #define ZSB_LN_WARPS_FULL 12
+#endif
 #define ZSB_LN_KERNEL inflate_lanes_small_kernel
 #define ZSB_LN_LAUNCH launch_inflate_lanes_small
 #define ZSB_LN_SECONDARY 1

@@ -32,7 +32,7 @@ constexpr int MAX_WARPS = 16;   // per CTA (= per SM): 118 registers per thread 
 #ifndef ZSB_LN_WARPS_FULL
 #define ZSB_LN_WARPS_FULL MAX_WARPS
 #endif
-size_t lane_smem(int warps, int segs_per_warp) { return sizeof(WarpScratch) + (size_t)warps * segs_per_warp * sizeof(LaneTables); }
+size_t lane_smem(int warps, int segs_per_warp, int nscratch) { return (size_t)nscratch * sizeof(WarpScratch) + (size_t)warps * segs_per_warp * sizeof(LaneTables); }
 
 __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 {
@@ -46,14 +46,15 @@ __device__ __forceinline__ void next_segment(Lane& L, const InflateParams& P)
 // segs_per_warp (S): lanes 0..S-1 decode a segment each, the others only help with the table builds.  Fewer segments
 // per warp = fewer divergent paths serialised per iteration and more warps for the same number of segments; the
 // launcher picks S from the number of segments so that the SMs have enough warps to hide latency.
-__global__ void __launch_bounds__(32 * MAX_WARPS) ZSB_LN_KERNEL(InflateParams P, uint8_t* scratch, int segs_per_warp)
+// nscratch: build scratches of the CTA; warp w uses scratch w % nscratch (behind its lock when it shares it).
+__global__ void __launch_bounds__(32 * MAX_WARPS) ZSB_LN_KERNEL(InflateParams P, uint8_t* scratch, int segs_per_warp, int nscratch)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    WarpScratch& sc = *reinterpret_cast<WarpScratch*>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& sc = reinterpret_cast<WarpScratch*>(smem)[warp % nscratch];
     const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    LaneTables* tabs = reinterpret_cast<LaneTables*>(smem + sizeof(WarpScratch)) + warp * segs_per_warp;
-    if (threadIdx.x == 0) sc.lock = 0;
+    LaneTables* tabs = reinterpret_cast<LaneTables*>(smem + (size_t)nscratch * sizeof(WarpScratch)) + warp * segs_per_warp;
+    if (threadIdx.x < nscratch) reinterpret_cast<WarpScratch*>(smem)[threadIdx.x].lock = 0;
     __syncthreads();
     uint8_t* my_scratch = scratch + (gwarp * 32 + lane) * SCRATCH_STRIDE;
     uint8_t* glens = my_scratch;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) ZSB_LN_KERNEL(InflateParams P,
         }
         // serve the lanes that wait for a table, one after the other, with the whole warp
         unsigned need = __ballot_sync(0xffffffffu, L.st == S_BUILD_BL || L.st == S_BUILD_LD);
-        const bool locked = need != 0 && blockDim.x > 32;
+        const bool locked = need != 0 && (int)(blockDim.x >> 5) > nscratch;
         if (locked) {   // the scratch is the CTA's: every word of it is written by the build before the build reads it
             if (lane == 0)
                 while (atomicCAS(&sc.lock, 0, 1) != 0) __nanosleep(200);
@@ -191,7 +192,7 @@ cudaError_t ZSB_LN_LAUNCH(const InflateParams& P, int num_sms, uint8_t* scratch,
     }
     // warps one SM holds with S segments per warp: shared memory for the tables, MAX_WARPS for the registers
     auto warps_per_sm = [&](int S) {
-        int w = (int)(((size_t)smem_max - sizeof(WarpScratch)) / ((size_t)S * sizeof(LaneTables)));
+        int w = (int)(((size_t)smem_max - sizeof(WarpScratch)) / ((size_t)S * sizeof(LaneTables)));   // with one scratch; more if room is left
         const char* e = getenv("ZSB_INFLATE_WARPS");   // experiments: cap the warps per SM
         const int cap = e ? atoi(e) : 0;
         if (cap >= 1 && w > cap) w = cap;
@@ -219,7 +220,14 @@ cudaError_t ZSB_LN_LAUNCH(const InflateParams& P, int num_sms, uint8_t* scratch,
         ctas = (int)((need + W - 1) / W);
     }
     if ((size_t)ctas * W * 32 * SCRATCH_STRIDE > scratch_bytes) return cudaErrorInvalidValue;
-    ZSB_LN_KERNEL<<<ctas, 32 * W, lane_smem(W, S), stream>>>(P, scratch, S);
+    // Build scratches: one per warp if shared memory has the room (the lanes of equal segments reach their block headers
+    // together, and a single scratch then serialises 7 x 32 builds: 32 768 segments 98 instead of 105 GB/s); but never across
+    // the 196 KiB carve-out step, which would halve the L1 (see ZSB_LN_WARPS_FULL).
+    const size_t tables = (size_t)W * S * sizeof(LaneTables), step = (size_t)195 * 1024;   // 196 KiB minus the 1 KiB the system reserves
+    const size_t limit = tables + sizeof(WarpScratch) <= step ? step : (size_t)smem_max;
+    int NS = (int)((limit - tables) / sizeof(WarpScratch));
+    NS = NS >= W ? W : 1;   // shared anyway: one scratch (four for twelve warps measured 141.5 against 143.1 GB/s at 16 GiB)
+    ZSB_LN_KERNEL<<<ctas, 32 * W, lane_smem(W, S, NS), stream>>>(P, scratch, S, NS);
     return cudaGetLastError();
 }
 

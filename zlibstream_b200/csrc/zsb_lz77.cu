@@ -680,7 +680,10 @@ __device__ uint2 slow_tile_search(const Smem& sm, int p, int hash_head, const Le
 // (hash << 10 | index) in shared memory (bitonic, 1024 keys; the tile_rec buffer of this tile is still free), then every
 // position finds its predecessor next to it.  Q2 is kept (no prev write when the value found is the position itself, which
 // happens for the position a refill pre-inserted, Q3), and the old content of every prev slot goes to the shadow first.
-__device__ void slow_tile_insert_sorted(const Smem& sm, int S, int T, int hash_variant, int ptid)
+// Returns (my_pos, my_head) = the position of sorted rank ptid and its predecessor, my_pos < 0 if there is none: the caller
+// searches THAT position, so that the lanes of a warp walk chains of the same or neighbouring hashes (similar lengths, the
+// same prev[] entries and candidates) instead of 32 unrelated ones.
+__device__ void slow_tile_insert_sorted(const Smem& sm, int S, int T, int hash_variant, int ptid, int& my_pos, int& my_head)
 {
     uint32_t* keys = reinterpret_cast<uint32_t*>(sm.tile_rec);   // 1024 x u32 <= WIDE_TILE x 8 bytes
     // Bitonic sort of 1024 keys by the first 512 producer threads, two adjacent keys (2t, 2t + 1) per thread: partners at
@@ -743,6 +746,8 @@ __device__ void slow_tile_insert_sorted(const Smem& sm, int S, int T, int hash_v
         if (pred != p) sm.prev[p & W_MASK] = (uint16_t)pred;
         if (my_last[m]) sm.head[my_h[m]] = (uint16_t)p;
     }
+    my_pos = my_on[0] ? my_p[0] : -1;
+    my_head = my_pred[0];
 }
 
 // (B) for the wide pipelined tile: slow_tile_search, except that a link whose prev[] slot has meanwhile been reused by a
@@ -1284,10 +1289,11 @@ __global__ void __launch_bounds__(NT, 1) lz77_segments_kernel(Lz77Params P)
                             smb.shadow = shadow_buf;
                             smb.shadow_lo = tS;
                             smb.shadow_hi = tS + tT;
-                            slow_tile_insert_sorted(smb, tS, tT, P.hash_variant, ptid);
+                            int my_pos, my_head;
+                            slow_tile_insert_sorted(smb, tS, tT, P.hash_variant, ptid, my_pos, my_head);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
                             const long long tp2 = P.stats ? clock64() : 0;
-                            if (ptid < tT) smb.tile_rec[ptid] = slow_tile_search_sh(smb, tS + ptid, smb.tile_hh[ptid], cfg);
+                            if (my_pos >= 0) smb.tile_rec[my_pos - tS] = slow_tile_search_sh(smb, my_pos, my_head, cfg);
                             asm volatile("bar.sync 3, 992;" ::: "memory");
                             if (ptid == 0) {
                                 __threadfence_block();

@@ -65,3 +65,12 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"oracle_lib|libzso|zso_|/oracle/|import oracle", t):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_bench_roofline_traffic_file_is_present():
+    """bench.py's roofline.traffic comes from the round's committed ncu capture; a missing key would silently report null."""
+    import json
+    t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    for key in ("deflate_config2", "inflate_config4"):
+        assert t[key]["dram_bytes_per_unit_byte"] > 0 and t[key]["unit_bytes_per_launch"] > 0
+        assert all(k["launches"] >= 1 for k in t[key]["kernels"].values())
